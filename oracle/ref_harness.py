@@ -1,0 +1,333 @@
+"""Pin the oracle against the reference's OWN modules (authoring container only).
+
+Imports `/root/reference/code/src/...` unmodified behind harness-side shims:
+  * `torch.Tensor.cuda` / `nn.Module.cuda` -> identity (the reference hard-codes `.cuda()`)
+  * stub modules `kaolin`, `trimesh`, `easydict`, `cv2`-free paths, `pytorch3d.ops.knn_points`
+    stand-in (squared L2 + topk, the documented contract of pytorch3d 35badc08)
+  * synthetic MANO-shaped struct fed to the vendored `lbs()` directly (MANO pickles are licensed)
+
+Usage:
+    python oracle/ref_harness.py check      # compare oracle vs reference, print max errors
+    python oracle/ref_harness.py golden     # (re)write tests/golden/*.pt from the REFERENCE modules
+
+`/root/reference` does not exist on the GPU box; nothing outside this script reads it.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, REPO)
+
+
+def install_shims():
+    if not os.path.isdir(REF):
+        raise RuntimeError("reference tree not present (this script runs in the authoring container only)")
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class EasyDict(dict):
+        def __init__(self, d=None, **kw):
+            super().__init__()
+            for k, v in {**(d or {}), **kw}.items():
+                self[k] = v
+
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    mod("easydict", EasyDict=EasyDict)
+    k = mod("kaolin")
+    k.ops = mod("kaolin.ops")
+    k.ops.mesh = mod("kaolin.ops.mesh", index_vertices_by_faces=lambda *a, **kw: None)
+    k.metrics = mod("kaolin.metrics")
+    k.metrics.trianglemesh = mod("kaolin.metrics.trianglemesh")
+    mod("trimesh")
+
+    def knn_points(p1, p2, K=1, return_nn=False, **kw):
+        d2 = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+        d, i = torch.topk(d2, K, dim=2, largest=False, sorted=True)
+        nn = torch.gather(p2[:, None].expand(-1, p1.shape[1], -1, -1), 2, i[..., None].expand(-1, -1, -1, 3))
+        return d, i, nn
+
+    p3d = mod("pytorch3d")
+    p3d.ops = mod("pytorch3d.ops", knn_points=knn_points)
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            mod("cv2")
+    sys.path.insert(0, os.path.join(REF, "code"))
+    sys.path.insert(0, REF)
+
+
+def ns(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def build_ref_node(sc, nid):
+    """Reference ImplicitNet / RenderingNet / density / sampler / deformer for one node of a SynthScene."""
+    from src.engine.density import LaplaceDensity
+    from src.engine.embedders import BarfEmbedder
+    from src.engine.ray_sampler import ErrorBoundSampler
+    from src.networks.shape_net import ImplicitNet
+    from src.networks.texture_net import RenderingNet
+
+    hand = nid in ("right", "left")
+    specs = ns(pose_dim=45 if hand else 0, embedding="fourier")
+    args = ns(barf_s=0, barf_e=10, no_barf=False)
+    iopt = ns(d_in=3, d_out=1, feature_vector_size=256, dims=[256] * 8, init="geometry", bias=0.6,
+              skip_in=[4], weight_norm=True, multires=6, cond="pose")
+    ropt = ns(feature_vector_size=256, mode="pose", d_in=14 + (0 if hand else 32), d_out=3,
+              dims=[256] * 4, weight_norm=True, multires_view=-1)
+    inet = ImplicitNet(iopt, args, specs)
+    rnet = RenderingNet(ropt, args, specs)
+    if not hand:  # object nodes embed with BARF (obj/specs.py:10); eval() => plain Fourier (render.py:43-47)
+        inet.embedder_obj = BarfEmbedder(3, 6, start=0, end=10, dev=torch.device("cpu"))
+        inet.embedder_obj.eval()
+    inet.load_state_dict(sc.sdf_state[nid], strict=False)  # embedder_obj.alpha_* buffers keep their init
+    rsd = dict(sc.rgb_state[nid])
+    if not hand:
+        rsd["lin_pose.weight"] = rnet.lin_pose.weight.data
+    rnet.load_state_dict(rsd, strict=True)
+    dens = LaplaceDensity(params_init={"beta": float(sc.beta[nid])}, beta_min=1e-4)
+    sampler = ErrorBoundSampler(sc.bounding_sphere, inverse_sphere_bg=True, N_samples_inverse_sphere=32, **sc.sampler)
+    inet.eval(), rnet.eval()
+    return inet, rnet, dens, sampler
+
+
+class _FakeServer:
+    pass
+
+
+def build_ref_deformer(sc, nid, art):
+    if nid in ("right", "left"):
+        from src.model.mano.deformer import KNNDeformer
+
+        d = KNNDeformer.__new__(KNNDeformer)
+        d.max_dist, d.K = 0.1, 15
+        d.verts = art[nid]["cano_verts"][None]
+        d.skin_weights = art[nid]["skin_W"][None]
+        return d
+    from src.model.obj.deformer import ObjectDeformer
+
+    return ObjectDeformer()
+
+
+def ref_servers(sc):
+    """Articulation from the reference's vendored lbs() / ObjectModel.forward."""
+    from src.utils.external.lbs import lbs
+    from src.model.obj.object_model import ObjectModel
+
+    art = {}
+    B = sc.B
+    scale = torch.full((B,), float(sc.scene_scale))
+    for nid in sc.node_ids:
+        p = sc.params[nid]
+        if nid in ("right", "left"):
+            m = sc.mano[nid]
+            pose_mean = torch.cat([torch.zeros(3), m["hands_mean"]])
+
+            def server(scene_scale, transl, thetas, betas, tfs_c_inv=None):
+                # GenericServer.forward (mano/server.py:62-99) with MANO.forward's pose_mean add
+                verts, joints, T_w, W, T, v_posed = lbs(betas, thetas + pose_mean, m["v_template"], m["shapedirs"],
+                                                        m["posedirs"], m["J_regressor"], m["parents"], m["lbs_weights"])
+                joints = torch.cat([joints, verts[:, m["tip_ids"]]], 1)
+                s = scene_scale.view(-1, 1, 1)
+                t = transl.view(-1, 1, 3)
+                out = {"verts": verts * s + t * s, "jnts": joints * s + t * s}
+                tf = T.clone()
+                tf[:, :, :3, :] = tf[:, :, :3, :] * s.view(-1, 1, 1, 1)
+                tf[:, :, :3, 3] = tf[:, :, :3, 3] + t * s
+                if tfs_c_inv is not None:
+                    tf = torch.einsum("bnij,njk->bnik", tf, tfs_c_inv)
+                out["tfs"], out["v_posed"] = tf, v_posed
+                return out
+
+            cano = server(torch.ones(1), torch.zeros(1, 3), torch.cat([torch.zeros(3), -m["hands_mean"]])[None],
+                          sc.betas[nid][None])
+            tfs_c_inv = cano["tfs"][0].inverse()
+            full_pose = torch.cat([p["global_orient"], p["pose"]], 1)
+            out = server(scale, p["transl"], full_pose, sc.betas[nid][None].repeat(B, 1), tfs_c_inv)
+            art[nid] = dict(kind="hand", tfs=out["tfs"], verts=out["verts"], jnts=out["jnts"], v_posed=out["v_posed"],
+                            cano_verts=cano["verts"][0], skin_W=m["lbs_weights"], pose_cond=full_pose[:, 3:] / math.pi)
+        else:
+            om = ObjectModel.__new__(ObjectModel)
+            torch.nn.Module.__init__(om)
+            om.register_buffer("obj_scale", torch.FloatTensor([1.0]))
+            om.register_buffer("v3d_cano", sc.obj_pts_cano)
+            om.register_buffer("norm_mat", torch.eye(4))
+            om.register_buffer("denorm_mat", torch.eye(4))
+            o = om.forward(p["global_orient"], p["transl"], scale)
+            art[nid] = dict(kind="object", tfs=o["T"], verts=o["vertices"])
+    return art
+
+
+def ref_render_scene(sc, ray_ids=None, chunk=None):
+    """The reference's own code path: get_camera_params -> ErrorBoundSampler.get_z_vals(sdf_func_with_deformer)
+    -> sdf_func_with_deformer -> render_color -> density -> merge_factors -> volumetric_render."""
+    import src.engine.volsdf_utils as vu
+    from src.datasets.utils import get_camera_params
+    from src.engine.rendering import render_color
+    from src.hold.hold_utils import merge_factors, volumetric_render
+
+    CLASS_ID = {"object": 1, "right": 2, "left": 3}
+    art = ref_servers(sc)
+    dirs, cam = get_camera_params(sc.uv, sc.extrinsics, sc.intrinsics)
+    P = dirs.shape[1]
+    dirs = dirs.reshape(-1, 3)
+    cam = cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3)
+    assert sc.B == 1 or ray_ids is None, "harness renders whole frames when B > 1"
+    if ray_ids is None:
+        ray_ids = torch.arange(dirs.shape[0])
+    chunk = chunk or ray_ids.numel()
+    nets = {nid: build_ref_node(sc, nid) for nid in sc.node_ids}
+    defs = {nid: build_ref_deformer(sc, nid, art) for nid in sc.node_ids}
+    outs = []
+    for s in range(0, ray_ids.numel(), chunk):
+        ids = ray_ids[s:s + chunk]
+        fl = []
+        for nid in sc.node_ids:
+            inet, rnet, dens, sampler = nets[nid]
+            a = art[nid]
+            hand = a["kind"] == "hand"
+            cond = {"pose": a["pose_cond"]} if hand else {"pose": torch.zeros(sc.B, 0)}
+            info = {"cond": cond, "tfs": a["tfs"]}
+            if hand:
+                info["verts"] = a["verts"]
+            d, c = dirs[ids], cam[ids]
+            z = sampler.get_z_vals(vu.sdf_func_with_deformer, defs[nid], inet, d, c, dens, False, info)
+            inet.eval()
+            S = z.shape[1]
+            pts = c.unsqueeze(1) + z.unsqueeze(2) * d.unsqueeze(1)
+            sdf, x_c, feat = vu.sdf_func_with_deformer(defs[nid], inet, False, pts.reshape(-1, 3), info)
+            tfs4 = a["tfs"] if hand else a["tfs"][:, None]
+            color, normal, sem = render_color(defs[nid], inet, rnet, d, cond, tfs4 if hand else a["tfs"][:, None],
+                                              x_c, feat, False, S, CLASS_ID[nid],
+                                              None if hand else sc.time_code)
+            density = dens(sdf).view(-1, S, 1)
+            fl.append({"color": color.detach(), "normal": normal.detach(), "density": density.detach(),
+                       "semantics": sem, "z_vals": z, "sdf": sdf.detach().reshape(-1, S),
+                       "canonical_pts": x_c.detach().reshape(-1, S, 3)})
+        core = [{k: f[k] for k in ("color", "normal", "density", "semantics", "z_vals")} for f in fl]
+        comp = merge_factors(core, check=True)
+        r = {"comp": dict(volumetric_render(comp, False))}
+        r["comp"]["z_vals"] = comp["z_vals"]
+        for k, f in enumerate(core):
+            f = dict(f)
+            f["z_max"] = f["z_vals"][:, -1]
+            r[k] = dict(volumetric_render(f, False))
+        outs.append(dict(nodes=fl, render=r))
+    return outs, art
+
+
+def _cmp(name, a, b, tol, w=None, tol_max=None):
+    """Comparison relative to the tensor's scale.
+
+    The pipeline is ill-conditioned *end to end*: the sampler's inverse-CDF has a flat PDF behind the
+    surface and a discontinuous `denom < 1e-5` branch (ray_sampler.py:304-305), so a 1e-6 change of one SDF
+    value (e.g. a different GEMM summation order) moves a few samples by ~1e-3 and a few pixels by ~3e-4.
+    End-to-end tensors are therefore held to: >= 97 % of entries within `tol`, and every entry (every entry with
+    reference weight > 1e-4 for per-sample tensors) within `tol_max` (default 30 tol).  Stage-wise parity
+    (same inputs per stage) is what is held to `tol` everywhere -- see tests/."""
+    a, b = a.detach().float(), b.detach().float()
+    d = (a - b).abs()
+    scale = max(b.abs().max().item(), 1.0)
+    tol_max = tol_max or 30 * tol
+    frac = (d <= tol * scale).float().mean().item()
+    if w is not None:
+        m = (w > 1e-4)
+        while m.dim() < d.dim():
+            m = m.unsqueeze(-1)
+        d = d * m
+    err = d.max().item()
+    ok = err <= tol_max * scale and frac >= 0.97
+    print(f"  {name:28s} max|d| {err:.3e}  within-tol {frac:.4f}  (scale {scale:.3e})  {'ok' if ok else 'MISMATCH'}")
+    return ok
+
+
+def check():
+    from hold_b200 import synth
+    from oracle import hold_oracle as O
+
+    ok = True
+    for cfgname, kw, beta in [("n2 beta.1", dict(H=12, W=12, S=128, nodes=("right", "object")), 0.1),
+                              ("n3 beta.03 S32", dict(H=8, W=8, S=32, nodes=("right", "left", "object")), 0.03),
+                              ("n2 B2", dict(H=6, W=6, S=128, nodes=("right", "object"), B=2), 0.05)]:
+        sc = synth.make_scene(**kw)
+        for nid in sc.node_ids:
+            sc.beta[nid] = torch.tensor(beta)
+        print(f"[{cfgname}]")
+        ro, ra = ref_render_scene(sc)
+        oo, oa = O.render_scene(sc)
+        for nid in sc.node_ids:
+            for k in ("tfs", "verts"):
+                ok &= _cmp(f"{nid}.{k}", oa[nid][k], ra[nid][k], 1e-5)
+            if nid != "object":
+                ok &= _cmp(f"{nid}.jnts", oa[nid]["jnts"], ra[nid]["jnts"], 1e-5)
+        for k, nid in enumerate(sc.node_ids):
+            wref = ro[0]["render"][k]["fg_weights"]
+            for key in ("z_vals", "sdf", "canonical_pts", "normal", "color", "density"):
+                ok &= _cmp(f"{nid}.{key}", oo[0]["nodes"][k][key], ro[0]["nodes"][k][key], 1e-4, wref)
+            for key in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
+                ok &= _cmp(f"{nid}.render.{key}", oo[0]["render"][k][key], ro[0]["render"][k][key], 1e-4)
+        for key in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
+            ok &= _cmp(f"comp.{key}", oo[0]["render"]["comp"][key], ro[0]["render"]["comp"][key], 1e-4)
+    print("ORACLE == REFERENCE" if ok else "ORACLE != REFERENCE")
+    return ok
+
+
+def golden():
+    """tests/golden/*.pt: inputs are regenerated from the seed; outputs come from the REFERENCE modules."""
+    from hold_b200 import synth
+
+    os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
+    cases = {
+        "c1_64x64_S32_n2": (dict(H=64, W=64, S=32, nodes=("right", "object"), seed=0), 0.1, 256),
+        "s128_n2_beta03": (dict(H=64, W=64, S=128, nodes=("right", "object"), seed=1), 0.03, 128),
+        "s128_n3_beta05": (dict(H=64, W=64, S=128, nodes=("right", "left", "object"), seed=2), 0.05, 96),
+    }
+    for name, (kw, beta, nrays) in cases.items():
+        sc = synth.make_scene(**kw)
+        for nid in sc.node_ids:
+            sc.beta[nid] = torch.tensor(beta)
+        g = torch.Generator().manual_seed(7)
+        ids = torch.sort(torch.randperm(kw["H"] * kw["W"], generator=g)[:nrays]).values
+        ro, ra = ref_render_scene(sc, ray_ids=ids)
+        rec = {"scene_kwargs": kw, "beta": beta, "ray_ids": ids, "nodes": {}, "render": {}, "art": {}}
+        for k, nid in enumerate(sc.node_ids):
+            n = ro[0]["nodes"][k]
+            rec["nodes"][nid] = {key: n[key].to(torch.float32).clone() for key in
+                                 ("z_vals", "sdf", "canonical_pts", "normal", "color", "density")}
+            rec["render"][nid] = {key: ro[0]["render"][k][key].clone() for key in
+                                  ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights")}
+            rec["art"][nid] = {key: ra[nid][key].clone() for key in ("tfs", "verts")}
+            if nid != "object":
+                rec["art"][nid]["jnts"] = ra[nid]["jnts"].clone()
+        rec["render"]["comp"] = {key: ro[0]["render"]["comp"][key].clone() for key in
+                                 ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights", "z_vals")}
+        path = os.path.join(REPO, "tests", "golden", name + ".pt")
+        torch.save(rec, path)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    install_shims()
+    torch.manual_seed(0)
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "check"
+    if cmd == "check":
+        sys.exit(0 if check() else 1)
+    elif cmd == "golden":
+        golden()
