@@ -1,0 +1,590 @@
+// C ABI of hold_b200 (include/hold_b200.h): context, weight packing, launch sequences.  Host-side logic
+// only — every arithmetic step of the path lives in the kernels included below.
+#include <stdarg.h>
+#include <new>
+
+#include "common.cuh"
+#include "geom.cuh"
+#include "sampler.cuh"
+#include "mlp_simt.cuh"
+#include "mlp_tc.cuh"
+#include "composite.cuh"
+
+namespace hold {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+enum WsSlot { WS_Z = 0, WS_SDF, WS_ZNEW, WS_SDFNEW, WS_BETA, WS_FAR, WS_XC, WS_SSDF, WS_GRAD, WS_FEAT, WS_PE, WS_ZTMP, WS_COUNT };
+
+static int ws_get(hold_ctx* ctx, int slot, size_t bytes, void** out) {
+  Buffer& b = ctx->ws[slot];
+  if (b.bytes < bytes) {
+    if (b.p) HOLD_CUDA(cudaFree(b.p));
+    b.p = nullptr, b.bytes = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+      return HOLD_E_NOMEM;
+    }
+    b.bytes = want;
+  }
+  *out = b.p;
+  return HOLD_OK;
+}
+#define WS(slot, type, count, var)                                                     \
+  type* var = nullptr;                                                                 \
+  {                                                                                    \
+    void* _p;                                                                          \
+    int _rc = ws_get(ctx, slot, sizeof(type) * (size_t)(count), &_p);                  \
+    if (_rc) return _rc;                                                               \
+    var = (type*)_p;                                                                   \
+  }
+
+static int dev_alloc(float** p, size_t n) {
+  if (*p) return HOLD_OK;
+  HOLD_CUDA(cudaMalloc((void**)p, n * sizeof(float)));
+  return HOLD_OK;
+}
+
+static int check_node(hold_ctx* ctx, int node, bool need_weights) {
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_REQUIRE(node >= 0 && node < HOLD_MAX_NODES, "node %d out of range", node);
+  if (!ctx->nodes[node].configured) { set_error("node %d not configured", node); return HOLD_E_STATE; }
+  if (need_weights && !ctx->nodes[node].has_weights) { set_error("node %d has no weights", node); return HOLD_E_STATE; }
+  return HOLD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MLP launches
+static int fill_sdf_args(const NodeState& ns, SimtArgs& a, bool jvp) {
+  a.n_layers = jvp ? 9 : 8;
+  for (int l = 0; l < a.n_layers; ++l) {
+    a.L[l].Wt = ns.sdf.Wt[l], a.L[l].bias = ns.sdf.bias[l], a.L[l].Kpad = ns.sdf.Kpad[l], a.L[l].N = ns.sdf.N[l];
+  }
+  a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
+  return HOLD_OK;
+}
+
+static int launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, const float* embed_w, float* sdf,
+                      float* grad, float* feat, const SamplerState* st, cudaStream_t s) {
+  if (P <= 0) return HOLD_OK;
+  const bool jvp = (grad != nullptr) || (feat != nullptr);
+  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
+  SimtArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_sdf_args(ns, a, jvp);
+  a.P = P, a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st;
+  if (jvp) {
+    HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
+    int tiles = ceil_div(P, kTileRows / 4);
+    k_mlp_simt<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), 256, kSimtSmemBytes, s>>>(a);
+  } else {
+    int tiles = ceil_div(P, kTileRows);
+    k_mlp_simt<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), 256, kSimtSmemBytes, s>>>(a);
+  }
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+static int launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame, const float* xc, const float* normal,
+                      const float* pe, const float* feat, const float* time_code, float* rgb, cudaStream_t s) {
+  if (P <= 0) return HOLD_OK;
+  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc_launch_rgb(ctx, ns, P, pts_per_frame, xc, normal, pe, feat, time_code, rgb, s);
+  SimtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_layers = 4;
+  for (int l = 0; l < 4; ++l) {
+    a.L[l].Wt = ns.rgb.Wt[l], a.L[l].bias = ns.rgb.bias[l], a.L[l].Kpad = ns.rgb.Kpad[l], a.L[l].N = ns.rgb.N[l];
+  }
+  a.w_last = ns.rgb.w_last, a.b_last = ns.rgb.b_last;
+  a.P = P, a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
+  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb;
+  int tiles = ceil_div(P, kTileRows);
+  k_mlp_simt<MLP_COLOR><<<min(tiles, ctx->sm_count), 256, kSimtSmemBytes, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_frame, bool from_z, int nsamp, int zstride,
+                               const float* zbuf, const float* cam, const float* dirs, const float* xin,
+                               const hold_node_pose* pose, float* xc, int* knn_idx, uint8_t* outlier,
+                               const SamplerState* st, cudaStream_t s) {
+  if (pts_per_frame <= 0 || B <= 0) return HOLD_OK;
+  dim3 grid(ceil_div(pts_per_frame, 128), B);
+  const bool hand = ns.cfg.kind == HOLD_KIND_HAND;
+  if (hand) {
+    HOLD_REQUIRE(pose->posed_verts != nullptr, "hand node needs posed_verts");
+    if (!ns.has_rig) { set_error("hand node has no rig (hold_node_set_rig)"); return HOLD_E_STATE; }
+  }
+#define IW(H, Z) k_inverse_warp<H, Z><<<grid, 128, 0, s>>>(pts_per_frame, nsamp, zstride, zbuf, cam, dirs, xin, pose->tfs, \
+                                                          pose->posed_verts, ns.skin_w, xc, knn_idx, outlier, st, ctx->dev_err)
+  if (hand && from_z) IW(true, true);
+  else if (hand) IW(true, false);
+  else if (from_z) IW(false, true);
+  else IW(false, false);
+#undef IW
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+}  // namespace hold
+
+using namespace hold;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int hold_version(void) { return HOLD_B200_VERSION; }
+const char* hold_last_error(void) { return g_err; }
+
+int hold_ctx_create(hold_ctx** out, int device) {
+  HOLD_REQUIRE(out != nullptr, "out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device: %s (hold_b200 has no CPU fallback)", cudaGetErrorString(e));
+    return HOLD_E_CUDA;
+  }
+  HOLD_REQUIRE(device >= 0 && device < count, "device %d out of range (%d devices)", device, count);
+  HOLD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HOLD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; hold_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return HOLD_E_CUDA;
+  }
+  hold_ctx* ctx = new (std::nothrow) hold_ctx();
+  if (!ctx) { set_error("out of host memory"); return HOLD_E_NOMEM; }
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  HOLD_CUDA(cudaMalloc((void**)&ctx->dev_err, sizeof(int)));
+  HOLD_CUDA(cudaMemset(ctx->dev_err, 0, sizeof(int)));
+  HOLD_CUDA(cudaFuncSetAttribute(k_mlp_simt<MLP_SDF_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSimtSmemBytes));
+  HOLD_CUDA(cudaFuncSetAttribute(k_mlp_simt<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSimtSmemBytes));
+  HOLD_CUDA(cudaFuncSetAttribute(k_mlp_simt<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSimtSmemBytes));
+  const int samp_smem = 4 * 6 * kMaxZ * (int)sizeof(float);
+  HOLD_CUDA(cudaFuncSetAttribute(k_sampler_merge_beta, cudaFuncAttributeMaxDynamicSharedMemorySize, samp_smem));
+  HOLD_CUDA(cudaFuncSetAttribute(k_sampler_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, samp_smem));
+  const int mano_smem = (2 * kVerts * 3 + kJoints * 3 + kJoints * 9 + 136 + 2 * kJoints * 16 + 16) * (int)sizeof(float);
+  (void)mano_smem;
+  int rc = tc_init(ctx);
+  if (rc) { delete ctx; return rc; }
+  *out = ctx;
+  return HOLD_OK;
+}
+
+int hold_ctx_destroy(hold_ctx* ctx) {
+  if (!ctx) return HOLD_OK;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 24; ++i)
+    if (ctx->ws[i].p) cudaFree(ctx->ws[i].p);
+  for (int n = 0; n < HOLD_MAX_NODES; ++n) {
+    NodeState& ns = ctx->nodes[n];
+    for (int l = 0; l < HOLD_MAX_LAYERS; ++l) {
+      if (ns.sdf.Wt[l]) cudaFree(ns.sdf.Wt[l]);
+      if (ns.sdf.bias[l]) cudaFree(ns.sdf.bias[l]);
+      if (ns.rgb.Wt[l]) cudaFree(ns.rgb.Wt[l]);
+      if (ns.rgb.bias[l]) cudaFree(ns.rgb.bias[l]);
+    }
+    float* ptrs[] = {ns.sdf.w_last, ns.sdf.b_last, ns.rgb.w_last, ns.rgb.b_last, ns.lin_pose_w, ns.lin_pose_b, ns.cano_verts, ns.skin_w};
+    for (float* p : ptrs)
+      if (p) cudaFree(p);
+    if (ns.sstate) cudaFree(ns.sstate);
+    tc_free(ns);
+  }
+  if (ctx->dev_err) cudaFree(ctx->dev_err);
+  delete ctx;
+  return HOLD_OK;
+}
+
+int hold_ctx_check(hold_ctx* ctx, void* stream) {
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  int h = 0;
+  HOLD_CUDA(cudaMemcpyAsync(&h, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  HOLD_CUDA(cudaStreamSynchronize(s));
+  if (h != 0) HOLD_CUDA(cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), s));
+  if (h & kErrRayMiss) { set_error("a ray misses the scene bounding sphere (engine/ray_sampler.py:15-18)"); return HOLD_E_RAY_MISSES_SPHERE; }
+  if (h & kErrNonFinite) { set_error("non-finite value (singular transform)"); return HOLD_E_NONFINITE; }
+  return HOLD_OK;
+}
+
+int64_t hold_ctx_launch_count(hold_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int hold_node_configure(hold_ctx* ctx, int node, const hold_node_cfg* cfg) {
+  HOLD_REQUIRE(ctx != nullptr && cfg != nullptr, "NULL argument");
+  HOLD_REQUIRE(node >= 0 && node < HOLD_MAX_NODES, "node %d out of range", node);
+  HOLD_REQUIRE(cfg->kind == HOLD_KIND_HAND || cfg->kind == HOLD_KIND_OBJECT, "bad kind %d", cfg->kind);
+  HOLD_REQUIRE(cfg->class_id >= 0 && cfg->class_id < 4, "class_id %d out of [0,4)", cfg->class_id);
+  HOLD_REQUIRE(cfg->n_samples_eval >= 2 && cfg->max_total_iters >= 1 && cfg->max_total_iters <= 8 &&
+                   cfg->n_samples_eval * cfg->max_total_iters <= kMaxZ,
+               "sampler buffer: n_samples_eval * max_total_iters must be <= %d", kMaxZ);
+  HOLD_REQUIRE(cfg->n_samples >= 1 && cfg->n_samples <= cfg->n_samples_eval * cfg->max_total_iters, "bad n_samples");
+  HOLD_REQUIRE(cfg->n_samples + cfg->n_samples_extra + 2 <= 512, "final sample count too large");
+  HOLD_REQUIRE(cfg->mlp_mode == HOLD_MLP_FP32 || cfg->mlp_mode == HOLD_MLP_TC, "bad mlp_mode");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  NodeState& ns = ctx->nodes[node];
+  ns.cfg = *cfg;
+  if (!ns.sstate) HOLD_CUDA(cudaMalloc((void**)&ns.sstate, sizeof(SamplerState)));
+  HOLD_CUDA(cudaMemset(ns.sstate, 0, sizeof(SamplerState)));
+  ns.configured = true;
+  return HOLD_OK;
+}
+
+int hold_node_set_weights(hold_ctx* ctx, int node, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb,
+                          const float* lin_pose_w, const float* lin_pose_b, void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  HOLD_REQUIRE(sdf != nullptr && rgb != nullptr, "NULL weights");
+  NodeState& ns = ctx->nodes[node];
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool hand = ns.cfg.kind == HOLD_KIND_HAND;
+  // ---- SDF net: dims [39(+45)] ->256 x3 -> 217 (+39) ->256 x4 -> 257 (networks/shape_net.py:13-49)
+  HOLD_REQUIRE(sdf->n_layers == 9, "SDF net must have 9 layers, got %d", sdf->n_layers);
+  HOLD_REQUIRE(sdf->in_dim[0] == (hand ? kEmbed + 45 : kEmbed), "SDF lin0 in_dim %d unexpected for this node kind", sdf->in_dim[0]);
+  for (int l = 0; l < 9; ++l) {
+    int eo = (l == 3) ? kHidden - kEmbed : (l == 8 ? kFeat + 1 : kHidden);
+    int ei = (l == 0) ? sdf->in_dim[0] : kHidden;
+    HOLD_REQUIRE(sdf->out_dim[l] == eo && sdf->in_dim[l] == ei, "SDF lin%d is %dx%d, expected %dx%d", l, sdf->out_dim[l], sdf->in_dim[l], eo, ei);
+    HOLD_REQUIRE(sdf->weight_v[l] && sdf->bias[l], "SDF lin%d has NULL tensors", l);
+  }
+  for (int l = 0; l < 9; ++l) {
+    int K = (l == 0) ? kEmbed : kHidden;
+    int Kpad = round_up(K, kKC);
+    int N = (l == 3) ? kHidden - kEmbed : kHidden;
+    int row_off = (l == 8) ? 1 : 0;  // lin8 row 0 is the sdf head, rows 1..256 the feature vector
+    ns.sdf.K[l] = K, ns.sdf.N[l] = N, ns.sdf.Kpad[l] = Kpad, ns.sdf.Npad[l] = 256;
+    rc = dev_alloc(&ns.sdf.Wt[l], (size_t)Kpad * 256);
+    if (rc) return rc;
+    rc = dev_alloc(&ns.sdf.bias[l], 256);
+    if (rc) return rc;
+    float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;  // skip_in: cat([x, input]) / sqrt(2)
+    k_pack_layer<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->bias[l], sdf->in_dim[l], row_off, 0, K, N,
+                                     Kpad, scale, ns.sdf.Wt[l], ns.sdf.bias[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  ns.sdf.n_layers = 9;
+  rc = dev_alloc(&ns.sdf.w_last, 256);
+  if (rc) return rc;
+  rc = dev_alloc(&ns.sdf.b_last, 4);
+  if (rc) return rc;
+  k_pack_rows<<<1, 128, 0, s>>>(sdf->weight_v[8], sdf->weight_g[8], sdf->bias[8], 256, 0, 1, ns.sdf.w_last, ns.sdf.b_last);
+  HOLD_LAUNCH_CHECK(ctx);
+  // ---- colour net: [270|302] -> 256 x4 -> 3 (networks/texture_net.py:13-44)
+  HOLD_REQUIRE(rgb->n_layers == 5, "colour net must have 5 layers, got %d", rgb->n_layers);
+  const int k0 = hand ? 270 : 302;
+  HOLD_REQUIRE(rgb->in_dim[0] == k0, "colour lin0 in_dim %d, expected %d", rgb->in_dim[0], k0);
+  for (int l = 0; l < 5; ++l) {
+    int eo = (l == 4) ? 3 : 256, ei = (l == 0) ? k0 : 256;
+    HOLD_REQUIRE(rgb->out_dim[l] == eo && rgb->in_dim[l] == ei, "colour lin%d is %dx%d, expected %dx%d", l, rgb->out_dim[l], rgb->in_dim[l], eo, ei);
+    HOLD_REQUIRE(rgb->weight_v[l] && rgb->bias[l], "colour lin%d has NULL tensors", l);
+  }
+  for (int l = 0; l < 4; ++l) {
+    int K = (l == 0) ? k0 : 256, Kpad = round_up(K, kKC);
+    ns.rgb.K[l] = K, ns.rgb.N[l] = 256, ns.rgb.Kpad[l] = Kpad, ns.rgb.Npad[l] = 256;
+    rc = dev_alloc(&ns.rgb.Wt[l], (size_t)Kpad * 256);
+    if (rc) return rc;
+    rc = dev_alloc(&ns.rgb.bias[l], 256);
+    if (rc) return rc;
+    k_pack_layer<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->bias[l], rgb->in_dim[l], 0, 0, K, 256, Kpad,
+                                     1.0f, ns.rgb.Wt[l], ns.rgb.bias[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  ns.rgb.n_layers = 5;
+  rc = dev_alloc(&ns.rgb.w_last, 3 * 256);
+  if (rc) return rc;
+  rc = dev_alloc(&ns.rgb.b_last, 4);
+  if (rc) return rc;
+  k_pack_rows<<<3, 128, 0, s>>>(rgb->weight_v[4], rgb->weight_g[4], rgb->bias[4], 256, 0, 3, ns.rgb.w_last, ns.rgb.b_last);
+  HOLD_LAUNCH_CHECK(ctx);
+  if (hand) {
+    HOLD_REQUIRE(lin_pose_w && lin_pose_b, "hand node needs lin_pose weights");
+    rc = dev_alloc(&ns.lin_pose_w, 8 * 45);
+    if (rc) return rc;
+    rc = dev_alloc(&ns.lin_pose_b, 8);
+    if (rc) return rc;
+    HOLD_CUDA(cudaMemcpyAsync(ns.lin_pose_w, lin_pose_w, 8 * 45 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    HOLD_CUDA(cudaMemcpyAsync(ns.lin_pose_b, lin_pose_b, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  rc = tc_pack(ctx, ns, sdf, rgb, s);
+  if (rc) return rc;
+  ns.has_weights = true;
+  return HOLD_OK;
+}
+
+int hold_node_set_rig(hold_ctx* ctx, int node, const float* cano_verts, const float* skin_weights, void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  HOLD_REQUIRE(cano_verts && skin_weights, "NULL rig tensors");
+  NodeState& ns = ctx->nodes[node];
+  HOLD_REQUIRE(ns.cfg.kind == HOLD_KIND_HAND, "only hand nodes have a rig");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = dev_alloc(&ns.cano_verts, kVerts * 3);
+  if (rc) return rc;
+  rc = dev_alloc(&ns.skin_w, kVerts * kJoints);
+  if (rc) return rc;
+  HOLD_CUDA(cudaMemcpyAsync(ns.cano_verts, cano_verts, kVerts * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemcpyAsync(ns.skin_w, skin_weights, kVerts * kJoints * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  ns.has_rig = true;
+  return HOLD_OK;
+}
+
+int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* betas, const float* full_pose,
+                  const float* transl, const float* scene_scale, const float* tfs_c_inv, float* verts, float* jnts,
+                  float* tfs, float* v_posed, void* stream) {
+  HOLD_REQUIRE(ctx && m, "NULL argument");
+  HOLD_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return HOLD_OK;
+  HOLD_REQUIRE(betas && full_pose && transl && scene_scale && verts && jnts && tfs && v_posed, "NULL tensor");
+  HOLD_REQUIRE(m->parents_host && m->tip_ids_host, "NULL host arrays in mano model");
+  ManoDev d;
+  d.v_template = m->v_template, d.shapedirs = m->shapedirs, d.posedirs = m->posedirs, d.J_regressor = m->J_regressor;
+  d.lbs_weights = m->lbs_weights, d.hands_mean = m->hands_mean;
+  for (int i = 0; i < kJoints; ++i) {
+    d.parents[i] = (i == 0) ? 0 : m->parents_host[i];
+    HOLD_REQUIRE(i == 0 || (d.parents[i] >= 0 && d.parents[i] < i), "parents must be topologically ordered");
+  }
+  for (int i = 0; i < 5; ++i) {
+    d.tips[i] = m->tip_ids_host[i];
+    HOLD_REQUIRE(d.tips[i] >= 0 && d.tips[i] < kVerts, "tip id out of range");
+  }
+  static bool attr_set = false;
+  const int smem = (2 * kVerts * 3 + kJoints * 3 + kJoints * 9 + 136 + 2 * kJoints * 16 + 16) * (int)sizeof(float);
+  if (!attr_set) {
+    HOLD_CUDA(cudaFuncSetAttribute(k_mano_lbs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_mano_lbs<<<B, 256, smem, (cudaStream_t)stream>>>(d, betas, full_pose, transl, scene_scale, tfs_c_inv, verts, jnts, tfs, v_posed);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_object_tf(hold_ctx* ctx, int B, const float* rot, const float* trans, const float* scene_scale, float obj_scale,
+                   const float* denorm_mat, const float* pts_cano, int Nv, float* tfs, float* verts, void* stream) {
+  HOLD_REQUIRE(ctx && rot && trans && scene_scale && denorm_mat && tfs, "NULL argument");
+  if (B <= 0) return HOLD_OK;
+  HOLD_REQUIRE(verts == nullptr || (pts_cano != nullptr && Nv > 0), "verts requested without canonical points");
+  dim3 grid(verts ? max(1, min(ceil_div(Nv, 128), 64)) : 1, B);
+  k_object_tf<<<grid, 128, 0, (cudaStream_t)stream>>>(B, Nv, rot, trans, scene_scale, obj_scale, denorm_mat, pts_cano, tfs, verts);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_camera_rays(hold_ctx* ctx, int B, int P, const float* uv, const float* pose, const float* intrinsics,
+                     float* ray_dirs, float* cam_loc, void* stream) {
+  HOLD_REQUIRE(ctx && uv && pose && intrinsics && ray_dirs && cam_loc, "NULL argument");
+  if (B * P <= 0) return HOLD_OK;
+  k_camera_rays<<<ceil_div(B * P, 256), 256, 0, (cudaStream_t)stream>>>(B, P, uv, pose, intrinsics, ray_dirs, cam_loc);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, const float* ray_dirs,
+                const hold_node_pose* pose, const hold_sampler_rand* rnd, float* z_vals, int32_t* iters, void* stream) {
+  int rc = check_node(ctx, node, true);
+  if (rc) return rc;
+  HOLD_REQUIRE(R >= 0 && B >= 1, "bad R/B");
+  if (R == 0) return HOLD_OK;
+  HOLD_REQUIRE(R % B == 0, "R (%d) must be B (%d) frames x rays, frame-major", R, B);
+  HOLD_REQUIRE(cam_loc && ray_dirs && pose && z_vals, "NULL argument");
+  HOLD_REQUIRE(pose->tfs && pose->beta_param, "pose needs tfs and beta_param");
+  NodeState& ns = ctx->nodes[node];
+  const hold_node_cfg& c = ns.cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ne = c.n_samples_eval;
+  WS(WS_Z, float, (size_t)R * kMaxZ, zb);
+  WS(WS_SDF, float, (size_t)R * kMaxZ, sb);
+  WS(WS_ZNEW, float, (size_t)R * Ne, znew);
+  WS(WS_SDFNEW, float, (size_t)R * Ne, sdfnew);
+  WS(WS_BETA, float, R, betab);
+  WS(WS_FAR, float, R, farb);
+  WS(WS_XC, float, (size_t)R * Ne * 3, xc);
+  SamplerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R, a.rays_per_frame = R / B;
+  a.n_eval = Ne, a.n_samples = c.n_samples, a.n_extra = c.n_samples_extra, a.beta_iters = c.beta_iters, a.max_iters = c.max_total_iters;
+  a.eps = c.eps, a.add_tiny = c.add_tiny, a.near = c.near, a.r_sphere = c.bounding_sphere, a.beta_min = c.beta_min;
+  a.cam = cam_loc, a.dirs = ray_dirs, a.beta_param = pose->beta_param;
+  a.z = zb, a.sdf = sb, a.znew = znew, a.sdfnew = sdfnew, a.beta = betab, a.far = farb, a.st = ns.sstate, a.err = ctx->dev_err;
+  if (rnd) { a.jitter = rnd->jitter, a.u_rand = rnd->u, a.extra_idx = rnd->extra_idx; }
+  a.z_out = z_vals, a.iters_out = iters;
+  const int wpb = 4;
+  const int samp_smem = wpb * 6 * kMaxZ * (int)sizeof(float);
+  k_sampler_init<<<ceil_div(R, wpb), wpb * 32, 0, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  for (int it = 0; it < c.max_total_iters; ++it) {
+    if (it > 0) {
+      k_round_gate<<<1, 1, 0, s>>>(ns.sstate, it, pose->beta_param, c.beta_min, c.max_total_iters);
+      HOLD_LAUNCH_CHECK(ctx);
+    }
+    rc = launch_inverse_warp(ctx, ns, B, (R / B) * Ne, true, Ne, Ne, znew, cam_loc, ray_dirs, nullptr, pose, xc, nullptr,
+                             nullptr, ns.sstate, s);
+    if (rc) return rc;
+    rc = launch_sdf(ctx, ns, R * Ne, xc, pose->embed_w, sdfnew, nullptr, nullptr, ns.sstate, s);
+    if (rc) return rc;
+    k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+    HOLD_LAUNCH_CHECK(ctx);
+    k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  return HOLD_OK;
+}
+
+int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_loc, const float* ray_dirs,
+               const hold_node_pose* pose, const hold_factors* out, void* stream) {
+  int rc = check_node(ctx, node, true);
+  if (rc) return rc;
+  HOLD_REQUIRE(R >= 0 && B >= 1 && S >= 1, "bad R/B/S");
+  if (R == 0) return HOLD_OK;
+  HOLD_REQUIRE(R % B == 0, "R (%d) must be B (%d) frames x rays, frame-major", R, B);
+  HOLD_REQUIRE(cam_loc && ray_dirs && pose && out, "NULL argument");
+  HOLD_REQUIRE(out->z_vals && out->color && out->normal && out->density, "factors need z_vals, color, normal, density");
+  HOLD_REQUIRE(pose->tfs && pose->beta_param, "pose needs tfs and beta_param");
+  NodeState& ns = ctx->nodes[node];
+  const bool hand = ns.cfg.kind == HOLD_KIND_HAND;
+  if (!hand) HOLD_REQUIRE(pose->time_code != nullptr, "object node needs time_code");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rpf = R / B;
+  const int max_pts = 1 << 20;
+  const int rays_per_chunk = max(1, min(rpf, max_pts / S));
+  const size_t cp = (size_t)rays_per_chunk * S;
+  WS(WS_XC, float, cp * 3 > (size_t)0 ? cp * 3 : 1, xc_ws);
+  WS(WS_SSDF, float, cp, sdf_ws);
+  WS(WS_GRAD, float, cp * 3, grad_ws);
+  WS(WS_FEAT, float, cp * kFeat, feat_ws);
+  float* pe = nullptr;
+  if (hand && pose->pose_cond != nullptr) {
+    WS(WS_PE, float, (size_t)B * 8, pe_ws);
+    pe = pe_ws;
+    k_pose_embed<<<ceil_div(B * 8, 64), 64, 0, s>>>(B, pose->pose_cond, ns.lin_pose_w, ns.lin_pose_b, pe);
+    HOLD_LAUNCH_CHECK(ctx);
+  } else if (hand) {
+    // RenderingNet with a 45-dim pose of zeros still applies lin_pose: embed = bias (texture_net.py:80-82)
+    HOLD_REQUIRE(false, "hand node needs pose_cond (pass zeros for the first 20 training epochs)");
+  }
+  for (int b = 0; b < B; ++b) {
+    hold_node_pose pb = *pose;
+    pb.tfs = pose->tfs + (size_t)b * (hand ? kJoints * 16 : 16);
+    if (hand) pb.posed_verts = pose->posed_verts + (size_t)b * kVerts * 3;
+    for (int r0 = 0; r0 < rpf; r0 += rays_per_chunk) {
+      const int rc_n = min(rays_per_chunk, rpf - r0);
+      const size_t ray0 = (size_t)b * rpf + r0;
+      const int P = rc_n * S;
+      float* xc = out->canonical_pts ? out->canonical_pts + ray0 * S * 3 : xc_ws;
+      float* sdf = out->sdf ? out->sdf + ray0 * S : sdf_ws;
+      rc = launch_inverse_warp(ctx, ns, 1, P, true, S, S, out->z_vals + ray0 * S, cam_loc + ray0 * 3, ray_dirs + ray0 * 3,
+                               nullptr, &pb, xc, nullptr, nullptr, nullptr, s);
+      if (rc) return rc;
+      rc = launch_sdf(ctx, ns, P, xc, pose->embed_w, sdf, grad_ws, feat_ws, nullptr, s);
+      if (rc) return rc;
+      dim3 grid(ceil_div(P, 128), 1);
+      if (hand)
+        k_normals_density<true><<<grid, 128, 0, s>>>(P, xc, grad_ws, sdf, pb.tfs, ns.cano_verts, ns.skin_w, pose->beta_param,
+                                                    ns.cfg.beta_min, out->normal + ray0 * S * 3, out->density + ray0 * S);
+      else
+        k_normals_density<false><<<grid, 128, 0, s>>>(P, xc, grad_ws, sdf, pb.tfs, nullptr, nullptr, pose->beta_param,
+                                                     ns.cfg.beta_min, out->normal + ray0 * S * 3, out->density + ray0 * S);
+      HOLD_LAUNCH_CHECK(ctx);
+      rc = launch_rgb(ctx, ns, P, P, xc, out->normal + ray0 * S * 3, pe ? pe + b * 8 : nullptr, feat_ws,
+                      hand ? nullptr : pose->time_code + b * 32, out->color + ray0 * S * 3, s);
+      if (rc) return rc;
+    }
+  }
+  return HOLD_OK;
+}
+
+int hold_composite(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors, const int32_t* class_ids_host,
+                   const hold_render_out* comp, const hold_render_out* per_node, void* stream) {
+  HOLD_REQUIRE(ctx && factors && class_ids_host, "NULL argument");
+  HOLD_REQUIRE(n >= 1 && n <= HOLD_MAX_NODES, "n = %d out of [1,%d]", n, HOLD_MAX_NODES);
+  HOLD_REQUIRE(R >= 0 && S >= 2, "bad R/S");
+  if (R == 0) return HOLD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  CompositeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R, a.S = S;
+  for (int k = 0; k < n; ++k) {
+    HOLD_REQUIRE(factors[k].color && factors[k].normal && factors[k].density && factors[k].z_vals, "factors[%d] incomplete", k);
+    HOLD_REQUIRE(class_ids_host[k] >= 0 && class_ids_host[k] < 4, "class id out of range");
+  }
+  if (comp != nullptr) {
+    a.n = n;
+    for (int k = 0; k < n; ++k) {
+      a.color[k] = factors[k].color, a.normal[k] = factors[k].normal, a.density[k] = factors[k].density, a.z[k] = factors[k].z_vals;
+      a.class_id[k] = class_ids_host[k];
+    }
+    a.out = *comp, a.drop_head = n - 1, a.drop_tail = n, a.single_zmax_last = 0;
+    k_composite<<<ceil_div(R, 128), 128, 0, s>>>(a);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  if (per_node != nullptr) {
+    for (int k = 0; k < n; ++k) {
+      CompositeArgs b;
+      memset(&b, 0, sizeof(b));
+      b.R = R, b.S = S, b.n = 1;
+      b.color[0] = factors[k].color, b.normal[0] = factors[k].normal, b.density[0] = factors[k].density, b.z[0] = factors[k].z_vals;
+      b.class_id[0] = class_ids_host[k];
+      b.out = per_node[k], b.drop_head = 0, b.drop_tail = 0, b.single_zmax_last = 1;
+      k_composite<<<ceil_div(R, 128), 128, 0, s>>>(b);
+      HOLD_LAUNCH_CHECK(ctx);
+    }
+  }
+  return HOLD_OK;
+}
+
+int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, int B, const float* cam_loc,
+                   const float* ray_dirs, const hold_node_pose* poses, const hold_factors* factors,
+                   const hold_render_out* comp, const hold_render_out* per_node, int32_t* iters, void* stream) {
+  HOLD_REQUIRE(ctx && node_ids_host && poses && factors, "NULL argument");
+  HOLD_REQUIRE(n >= 1 && n <= HOLD_MAX_NODES, "n = %d out of [1,%d]", n, HOLD_MAX_NODES);
+  int32_t cls[HOLD_MAX_NODES];
+  int S = -1;
+  for (int k = 0; k < n; ++k) {
+    int node = node_ids_host[k];
+    int rc = check_node(ctx, node, true);
+    if (rc) return rc;
+    const hold_node_cfg& c = ctx->nodes[node].cfg;
+    int Sk = c.n_samples + c.n_samples_extra + 2;
+    HOLD_REQUIRE(S < 0 || S == Sk, "all nodes must produce the same number of samples per ray");
+    S = Sk;
+    cls[k] = c.class_id;
+  }
+  for (int k = 0; k < n; ++k) {
+    int rc = hold_sample(ctx, node_ids_host[k], R, B, cam_loc, ray_dirs, &poses[k], nullptr, factors[k].z_vals,
+                         iters ? iters + k : nullptr, stream);
+    if (rc) return rc;
+    rc = hold_shade(ctx, node_ids_host[k], R, B, S, cam_loc, ray_dirs, &poses[k], &factors[k], stream);
+    if (rc) return rc;
+  }
+  return hold_composite(ctx, n, R, S, factors, cls, comp, per_node, stream);
+}
+
+int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c, const float* embed_w, float* sdf, float* grad,
+                  float* feat, void* stream) {
+  int rc = check_node(ctx, node, true);
+  if (rc) return rc;
+  HOLD_REQUIRE(P >= 0, "negative P");
+  if (P == 0) return HOLD_OK;
+  HOLD_REQUIRE(x_c && sdf, "NULL argument");
+  HOLD_REQUIRE((grad == nullptr) == (feat == nullptr), "grad and feat must be requested together");
+  return launch_sdf(ctx, ctx->nodes[node], P, x_c, embed_w, sdf, grad, feat, nullptr, (cudaStream_t)stream);
+}
+
+int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose, float* x_c,
+                      int32_t* knn_idx, uint8_t* outlier_mask, void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  HOLD_REQUIRE(B >= 0 && P >= 0, "negative size");
+  if (B * P == 0) return HOLD_OK;
+  HOLD_REQUIRE(x && pose && x_c && pose->tfs, "NULL argument");
+  return launch_inverse_warp(ctx, ctx->nodes[node], B, P, false, 1, 1, nullptr, nullptr, nullptr, x, pose, x_c, knn_idx,
+                             outlier_mask, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// hold_b200 — shared declarations for the sm_100a kernels behind include/hold_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hold_b200.h"
+
+namespace hold {
+
+constexpr int kVerts = 778;    // MANO vertices
+constexpr int kJoints = 16;    // MANO bones (num_full_tfs, model/mano/specs.py)
+constexpr int kKnn = 15;       // MANODeformer K (mano_node.py:28)
+constexpr int kEmbed = 39;     // 3 + 3*2*6 (engine/embedders.py:21-41, multires 6)
+constexpr int kFeat = 256;     // feature_vector_size
+constexpr int kHidden = 256;
+constexpr int kMaxZ = 640;     // n_samples_eval * max_total_iters upper bound supported by the sampler kernels
+constexpr int kSdfLayers = 9;
+constexpr int kRgbLayers = 5;
+
+// device error word bits
+constexpr int kErrRayMiss = 1;
+constexpr int kErrNonFinite = 2;
+
+struct SamplerState {  // device-resident, one per node; written only by single-thread epilogues
+  int iters;           // rounds executed so far
+  int done;            // 1 once the final sample set has been produced
+  unsigned beta_max_bits[8];  // per round: max over rays of beta (float bits, positive => monotone)
+};
+
+struct PackedMlp {           // fp32 CUDA-core layout: Wt[l] is [Kpad][Npad] (k-major rows, n contiguous)
+  int n_layers = 0;
+  int K[HOLD_MAX_LAYERS], N[HOLD_MAX_LAYERS], Kpad[HOLD_MAX_LAYERS], Npad[HOLD_MAX_LAYERS];
+  float* Wt[HOLD_MAX_LAYERS] = {nullptr};
+  float* bias[HOLD_MAX_LAYERS] = {nullptr};
+  float* w_last = nullptr;   // SDF: row 0 of the last layer (the sdf output) [256]; RGB: last layer [3][256]
+  float* b_last = nullptr;
+};
+
+struct TcMlp;  // tcgen05 packing, mlp_tc.cuh
+
+struct NodeState {
+  bool configured = false, has_weights = false, has_rig = false;
+  hold_node_cfg cfg;
+  PackedMlp sdf, rgb;
+  TcMlp* tc = nullptr;
+  float* lin_pose_w = nullptr;  // [8,45]
+  float* lin_pose_b = nullptr;  // [8]
+  float* cano_verts = nullptr;  // [778,3]
+  float* skin_w = nullptr;      // [778,16]
+  SamplerState* sstate = nullptr;
+};
+
+struct Buffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace hold
+
+struct hold_ctx {
+  int device = 0;
+  int sm_count = 148;
+  hold::NodeState nodes[HOLD_MAX_NODES];
+  int* dev_err = nullptr;
+  int64_t launches = 0;
+  hold::Buffer ws[24];  // grow-only workspaces, indexed by purpose (api.cu)
+};
+
+namespace hold {
+
+void set_error(const char* fmt, ...);
+#define HOLD_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      hold::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return HOLD_E_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+#define HOLD_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      hold::set_error(__VA_ARGS__);  \
+      return HOLD_E_BADARG;          \
+    }                                \
+  } while (0)
+#define HOLD_LAUNCH_CHECK(ctx)       \
+  do {                               \
+    (ctx)->launches++;               \
+    HOLD_CUDA(cudaPeekAtLastError()); \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// torch.linspace(start, end, steps)[i] in fp32 — symmetric evaluation like ATen's linspace kernel
+// (RangeFactories: first half from start, second half from end).
+__host__ __device__ inline float torch_linspace(float start, float end, int steps, int i) {
+  if (steps == 1) return start;
+  float step = (end - start) / (float)(steps - 1);
+  int half = steps / 2;
+  return (i < half) ? (start + step * (float)i) : (end - step * (float)(steps - i - 1));
+}
+
+// LaplaceDensity.density_func (engine/density.py:21-26)
+__device__ inline float laplace_density(float s, float beta) {
+  float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  return (1.0f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(s) / beta));
+}
+
+}  // namespace hold

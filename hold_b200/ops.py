@@ -1,0 +1,72 @@
+"""Stage-level entry points (thin wrappers over the C ABI) used by tests and by callers that drive the
+stages themselves: shade (Node.forward after sampling) and composite (merge_factors + volumetric_render)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .capi import Factors, NodePose, RenderOut, check, lib, ptr, stream_ptr
+
+
+def camera_rays(ctx, uv, pose, intrinsics):
+    B, P, _ = uv.shape
+    dirs = torch.empty(B * P, 3, device=uv.device)
+    cam = torch.empty(B * P, 3, device=uv.device)
+    check(lib().hold_camera_rays(ctx.h, B, P, ptr(uv.float().contiguous()), ptr(pose.float().contiguous()),
+                                 ptr(intrinsics.float().contiguous()), ptr(dirs), ptr(cam), stream_ptr()))
+    return dirs, cam
+
+
+def shade(node, ray_dirs, cam_loc, pose: NodePose, z_vals, B: int):
+    R, S = z_vals.shape
+    dev = z_vals.device
+    t = dict(color=torch.empty(R, S, 3, device=dev), normal=torch.empty(R, S, 3, device=dev), density=torch.empty(R, S, device=dev),
+             z_vals=z_vals.contiguous(), sdf=torch.empty(R, S, device=dev), canonical_pts=torch.empty(R, S, 3, device=dev))
+    f = Factors()
+    for k, v in t.items():
+        setattr(f, k, v.data_ptr())
+    check(lib().hold_shade(node.ctx.h, node.slot, R, B, S, ptr(cam_loc), ptr(ray_dirs), C.byref(pose), C.byref(f), stream_ptr()))
+    return t
+
+
+def composite(ctx, factors: list, class_ids: list, want_weights=True):
+    n = len(factors)
+    R, S = factors[0]["z_vals"].shape
+    dev = factors[0]["z_vals"].device
+    facs = (Factors * n)()
+    keep = []
+    for k, f in enumerate(factors):
+        for kk in ("color", "normal", "density", "z_vals"):
+            v = f[kk].float().contiguous()
+            keep.append(v)
+            setattr(facs[k], kk, v.data_ptr())
+
+    def mk(m):
+        t = dict(fg_rgb=torch.empty(R, 3, device=dev), mask_prob=torch.empty(R, device=dev), normal=torch.empty(R, 3, device=dev),
+                 depth=torch.empty(R, device=dev), fg_semantics=torch.empty(R, 4, device=dev), bg_weights=torch.empty(R, device=dev))
+        if want_weights:
+            t["fg_weights"] = torch.empty(R, m, device=dev)
+        ro = RenderOut()
+        for kk, v in t.items():
+            setattr(ro, kk, v.data_ptr())
+        return ro, t
+
+    comp, comp_t = mk(n * S - 2 * n + 1)
+    per = (RenderOut * n)()
+    per_t = []
+    for k in range(n):
+        per[k], t = mk(S)
+        per_t.append(t)
+    cls = (C.c_int32 * n)(*class_ids)
+    check(lib().hold_composite(ctx.h, n, R, S, facs, cls, C.byref(comp), per, stream_ptr()))
+    return comp_t, per_t
+
+
+def inverse_warp(node, x, pose: NodePose, want_idx=False):
+    B, P, _ = x.shape
+    xc = torch.empty(B, P, 3, device=x.device)
+    idx = torch.empty(B, P, 15, dtype=torch.int32, device=x.device) if want_idx else None
+    mask = torch.empty(B, P, dtype=torch.uint8, device=x.device) if want_idx else None
+    check(lib().hold_inverse_warp(node.ctx.h, node.slot, B, P, ptr(x.float().contiguous()), C.byref(pose), ptr(xc), ptr(idx), ptr(mask), stream_ptr()))
+    return xc, idx, mask

@@ -1,0 +1,193 @@
+/* hold_b200 — C ABI of the B200-native HOLD volumetric-rendering hot path.
+ *
+ * The reference (zc-alexfan/hold) has no FFI/plugin layer: its call surface for this path is a set of
+ * Python classes.  Each entry point below replaces the body of one of them; the
+ * reference-side binding (a ctypes stub inside the unchanged Python class) is shown in INTEGRATION.md.
+ * All file:line citations are relative to /root/reference/code/src.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous row-major fp32 unless the name ends in `_host`
+ *    or the comment says otherwise; integer outputs are int32;
+ *  - every call enqueues on `stream` (a cudaStream_t passed as void*) and never synchronises the host —
+ *    including the sampler's batch-global convergence flag (engine/ray_sampler.py:244);
+ *  - the caller owns all input/output buffers; the library owns only its workspace and packed weights;
+ *  - return value: 0 on success, a negative hold_status otherwise; text via hold_last_error();
+ *  - never exit()/abort (contrast engine/ray_sampler.py:16-18).
+ */
+#ifndef HOLD_B200_H
+#define HOLD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOLD_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum hold_status {
+  HOLD_OK = 0,
+  HOLD_E_BADARG = -1,
+  HOLD_E_CUDA = -2,
+  HOLD_E_RAY_MISSES_SPHERE = -3, /* reported by hold_ctx_check(), engine/ray_sampler.py:15-18 */
+  HOLD_E_NONFINITE = -4,
+  HOLD_E_NOMEM = -5,
+  HOLD_E_STATE = -6
+} hold_status;
+
+typedef struct hold_ctx hold_ctx;
+
+enum { HOLD_KIND_HAND = 0, HOLD_KIND_OBJECT = 1 };
+/* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 bf16x3 split precision (fp32 accumulate). */
+enum { HOLD_MLP_FP32 = 0, HOLD_MLP_TC = 1 };
+enum { HOLD_MAX_NODES = 4, HOLD_MAX_LAYERS = 9 };
+
+/* Node.__init__ + confs/general.yaml `ray_sampler`/`implicit_network` constants
+ * (model/renderables/node.py:17-47; engine/ray_sampler.py:89-126). */
+typedef struct hold_node_cfg {
+  int32_t kind;            /* HOLD_KIND_* */
+  int32_t class_id;        /* semantics channel: object 1, right 2, left 3 (engine/rendering.py:59-61) */
+  int32_t n_samples_eval;  /* N_samples_eval (128) */
+  int32_t n_samples;       /* N_samples (64) */
+  int32_t n_samples_extra; /* N_samples_extra (32) */
+  int32_t beta_iters;      /* 10 */
+  int32_t max_total_iters; /* 5 */
+  int32_t mlp_mode;        /* HOLD_MLP_* */
+  float eps;               /* 0.1 */
+  float add_tiny;          /* 1e-6 */
+  float near;              /* 0.0 */
+  float bounding_sphere;   /* scene_bounding_sphere */
+  float beta_min;          /* LaplaceDensity beta_min, 1e-4 (engine/density.py:17-19) */
+} hold_node_cfg;
+
+/* One MLP in the reference's state_dict layout: lin<k>.weight_v [out,in], lin<k>.weight_g [out,1],
+ * lin<k>.bias [out] (networks/shape_net.py:79-81, texture_net.py:39-41).  weight_g may be NULL for a
+ * layer without weight-norm (then weight_v is the plain weight). */
+typedef struct hold_mlp_weights {
+  int32_t n_layers;
+  int32_t in_dim[HOLD_MAX_LAYERS];
+  int32_t out_dim[HOLD_MAX_LAYERS];
+  const float* weight_v[HOLD_MAX_LAYERS];
+  const float* weight_g[HOLD_MAX_LAYERS];
+  const float* bias[HOLD_MAX_LAYERS];
+} hold_mlp_weights;
+
+/* MANO model tensors (utils/external/body_models.py:502-560; lbs() arguments utils/external/lbs.py:139-151). */
+typedef struct hold_mano_model {
+  const float* v_template;  /* [778,3] */
+  const float* shapedirs;   /* [778,3,10] */
+  const float* posedirs;    /* [135,2334] */
+  const float* J_regressor; /* [16,778] */
+  const float* lbs_weights; /* [778,16] */
+  const float* hands_mean;  /* [45] (pose_mean = [0,0,0,hands_mean], flat_hand_mean=False) */
+  const int32_t* parents_host; /* [16] HOST pointer, parents[0] = -1 */
+  const int32_t* tip_ids_host; /* [5]  HOST pointer (vertex_ids 'mano') */
+} hold_mano_model;
+
+/* Per-call articulation of one node, as produced by the servers (a16/a17). */
+typedef struct hold_node_pose {
+  const float* tfs;         /* hand: [B,16,4,4] (relative to canonical); object: [B,4,4] */
+  const float* posed_verts; /* hand: [B,778,3] (deform_info["verts"]); object: NULL */
+  const float* pose_cond;   /* hand: [B,45] = full_pose[:,3:]/pi (or zeros), object: NULL */
+  const float* time_code;   /* object: [B,32] frame latent; hand: NULL */
+  const float* embed_w;     /* [39] BARF weights or NULL (plain Fourier) */
+  const float* beta_param;  /* [1] density.beta parameter (device scalar) */
+} hold_node_pose;
+
+/* Outputs of Node.forward (`factors`, model/renderables/node.py:78-86) for R rays x S samples. */
+typedef struct hold_factors {
+  float* color;         /* [R,S,3] */
+  float* normal;        /* [R,S,3] */
+  float* density;       /* [R,S]   */
+  float* z_vals;        /* [R,S]   */
+  float* sdf;           /* [R,S]   optional (may be NULL) */
+  float* canonical_pts; /* [R,S,3] optional */
+} hold_factors;
+
+/* Outputs of volumetric_render (hold/hold_utils.py:243-271). Any pointer may be NULL to skip it. */
+typedef struct hold_render_out {
+  float* fg_rgb;       /* [R,3] */
+  float* mask_prob;    /* [R]   */
+  float* normal;       /* [R,3] */
+  float* depth;        /* [R]   */
+  float* fg_semantics; /* [R,4] */
+  float* bg_weights;   /* [R]   */
+  float* fg_weights;   /* [R,S_out] */
+} hold_render_out;
+
+/* Training-mode randomness is an INPUT (generated by torch on the host side of the boundary):
+ * stratified jitter (ray_sampler.py:70-78), u (:292), extras permutation (:328).  All NULL in eval. */
+typedef struct hold_sampler_rand {
+  const float* jitter;      /* [R, n_samples_eval] uniforms */
+  const float* u;           /* [R, n_samples] uniforms */
+  const int32_t* extra_idx; /* [n_samples_extra] indices into the final z buffer */
+} hold_sampler_rand;
+
+int hold_version(void);
+const char* hold_last_error(void); /* thread-local */
+int hold_ctx_create(hold_ctx** out, int device);
+int hold_ctx_destroy(hold_ctx* ctx);
+/* Synchronises `stream` and reads the device error word (ray missed the bounding sphere, non-finite). */
+int hold_ctx_check(hold_ctx* ctx, void* stream);
+/* Number of kernels this library launched since the ctx was created (bench.py's gpu_launches). */
+int64_t hold_ctx_launch_count(hold_ctx* ctx);
+
+int hold_node_configure(hold_ctx* ctx, int node, const hold_node_cfg* cfg);
+/* Fold weight-norm (shape_net.py:80), drop the hand's 45 zeroed pose columns (shape_net.py:104-106),
+ * pre-scale the skip layer by 1/sqrt(2) (shape_net.py:122), pack for both MLP modes.  Re-call after
+ * every optimiser step / load_state_dict.  lin_pose_* : RenderingNet.lin_pose (texture_net.py:32-37). */
+int hold_node_set_weights(hold_ctx* ctx, int node, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb,
+                          const float* lin_pose_w, const float* lin_pose_b, void* stream);
+/* Canonical rig of a hand node: KNNDeformer.verts / .skin_weights (model/mano/deformer.py:17-32). */
+int hold_node_set_rig(hold_ctx* ctx, int node, const float* cano_verts /*[778,3]*/,
+                      const float* skin_weights /*[778,16]*/, void* stream);
+
+/* a16: GenericServer.forward (model/mano/server.py:62-99) = MANO lbs() + scene scaling + tfs_c_inv.
+ * tfs_c_inv NULL <=> absolute=True.  Outputs: verts [B,778,3], jnts [B,21,3], tfs [B,16,4,4], v_posed [B,778,3]. */
+int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* betas /*[B,10]*/,
+                  const float* full_pose /*[B,48]*/, const float* transl /*[B,3]*/, const float* scene_scale /*[B]*/,
+                  const float* tfs_c_inv /*[16,4,4] or NULL*/, float* verts, float* jnts, float* tfs, float* v_posed,
+                  void* stream);
+/* a17: ObjectModel.forward (model/obj/object_model.py:29-70). */
+int hold_object_tf(hold_ctx* ctx, int B, const float* rot /*[B,3]*/, const float* trans /*[B,3]*/,
+                   const float* scene_scale /*[B]*/, float obj_scale, const float* denorm_mat /*[4,4]*/,
+                   const float* pts_cano /*[Nv,3]*/, int Nv, float* tfs /*[B,4,4]*/, float* verts /*[B,Nv,3] or NULL*/,
+                   void* stream);
+/* a1: get_camera_params (datasets/utils.py:255-282): uv [B,P,2], pose [B,4,4], K [B,4,4] ->
+ * ray_dirs [B*P,3], cam_loc [B*P,3] (cam_loc repeated per ray as mano_node.py:90-92). */
+int hold_camera_rays(hold_ctx* ctx, int B, int P, const float* uv, const float* pose, const float* intrinsics,
+                     float* ray_dirs, float* cam_loc, void* stream);
+
+/* a4: ErrorBoundSampler.get_z_vals (engine/ray_sampler.py:128-352) driving sdf_func_with_deformer
+ * (engine/volsdf_utils.py:150-169).  R rays = B frames x R/B rays, frame-major.
+ * z_vals [R, n_samples + n_samples_extra + 2]; iters: device int32 = rounds executed (batch-global). */
+int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, const float* ray_dirs,
+                const hold_node_pose* pose, const hold_sampler_rand* rnd, float* z_vals, int32_t* iters,
+                void* stream);
+/* a5+a10+a11+a12: Node.forward after sampling (node.py:55-86): inverse warp, SDF + feature + gradient,
+ * forward-skinning Jacobian, normals, colour net, Laplace density.  out->z_vals is an INPUT here. */
+int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_loc, const float* ray_dirs,
+               const hold_node_pose* pose, const hold_factors* out, void* stream);
+/* a13+a14: merge_factors + volumetric_render for the composite and for each node
+ * (hold/hold_net.py:76-88).  comp_S = n*S - 2n + 1.  per_node[k] may be NULL. */
+int hold_composite(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors /*[n]*/,
+                   const int32_t* class_ids_host /*[n]*/, const hold_render_out* comp,
+                   const hold_render_out* per_node /*[n] or NULL*/, void* stream);
+/* a18 (foreground): the whole path for n nodes, one call, no host sync. node_ids[k] are ctx node slots. */
+int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, int B, const float* cam_loc,
+                   const float* ray_dirs, const hold_node_pose* poses /*[n]*/, const hold_factors* factors /*[n]*/,
+                   const hold_render_out* comp, const hold_render_out* per_node /*[n] or NULL*/,
+                   int32_t* iters /*[n] device*/, void* stream);
+
+/* Building blocks exported for tests and for callers that hold canonical points already
+ * (hold_utils.query_oc, meshing): ImplicitNet.forward on canonical points (shape_net.py:84-130). */
+int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c /*[P,3]*/, const float* embed_w,
+                  float* sdf /*[P]*/, float* grad /*[P,3] or NULL*/, float* feat /*[P,256] or NULL*/, void* stream);
+/* KNNDeformer.forward(inverse=True) / ObjectDeformer.forward(inverse=True): x [B,P,3] -> x_c, knn idx [B,P,15] (opt). */
+int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose,
+                      float* x_c, int32_t* knn_idx, uint8_t* outlier_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLD_B200_H */

@@ -1,0 +1,46 @@
+"""End-to-end parity of hold_render_fg (through the host mirror) against the committed golden fixtures,
+which were produced by the REFERENCE's own modules (oracle/ref_harness.py golden)."""
+import glob
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+def e2e_close(a, b, name, tol=1e-4, tol_max=3e-3):
+    a, b = a.detach().float().cpu().reshape(b.shape), b.float()
+    scale = max(1.0, b.abs().max().item())
+    d = (a - b).abs()
+    frac = (d <= tol * scale).float().mean().item()
+    assert frac >= 0.97, f"{name}: only {frac:.4f} within {tol}"
+    assert d.max().item() <= tol_max * scale, f"{name}: max|d| {d.max().item():.3e}"
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-3] for p in GOLD])
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_golden(path, mode, ctx):
+    from hold_b200 import capi, scene_io, synth
+
+    if mode == "tc" and not getattr(capi, "TC_READY", False):
+        pytest.skip("tcgen05 MLP path not enabled in this build")
+    rec = torch.load(path)
+    sc = synth.make_scene(**rec["scene_kwargs"])
+    for nid in sc.node_ids:
+        sc.beta[nid] = torch.tensor(rec["beta"])
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC if mode == "tc" else capi.MLP_FP32)
+    dev = torch.device("cuda", 0)
+    out = net.forward_fg(scene_io.scene_input(sc, dev, ray_ids=rec["ray_ids"]))
+    ctx.check()
+    for nid in sc.node_ids:
+        art = out["articulation"][nid]
+        e2e_close(art["verts"], rec["art"][nid]["verts"], f"{nid}.verts", 1e-5, 1e-4)
+        if nid != "object":
+            e2e_close(art["tfs"], rec["art"][nid]["tfs"], f"{nid}.tfs", 1e-5, 1e-4)
+            e2e_close(art["jnts"], rec["art"][nid]["jnts"], f"{nid}.jnts", 1e-5, 1e-4)
+        for k in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
+            e2e_close(out[f"{nid}.{k}"], rec["render"][nid][k], f"{nid}.{k}")
+    for k in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
+        e2e_close(out[k], rec["render"]["comp"][k], f"comp.{k}")
