@@ -565,6 +565,14 @@ int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, in
   return hold_composite(ctx, n, R, S, factors, cls, comp, per_node, stream);
 }
 
+/* debug/test hook (not in the public header): workspace slot pointers of the last call */
+int hold_debug_ws_copy(hold_ctx* ctx, int slot, void* dst, size_t bytes) {
+  if (!ctx || slot < 0 || slot >= 24 || ctx->ws[slot].bytes < bytes) return HOLD_E_BADARG;
+  HOLD_CUDA(cudaDeviceSynchronize());
+  HOLD_CUDA(cudaMemcpy(dst, ctx->ws[slot].p, bytes, cudaMemcpyDeviceToDevice));
+  return HOLD_OK;
+}
+
 int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c, const float* embed_w, float* sdf, float* grad,
                   float* feat, void* stream) {
   int rc = check_node(ctx, node, true);

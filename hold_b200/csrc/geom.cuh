@@ -151,9 +151,11 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
     size_t ray = gp / ns;
     int k = (int)(gp - ray * ns);
     float t = zbuf[ray * zstride + k];
-    x = cam[3 * ray] + t * dirs[3 * ray];
-    y = cam[3 * ray + 1] + t * dirs[3 * ray + 1];
-    z = cam[3 * ray + 2] + t * dirs[3 * ray + 2];
+    // mul then add, no FMA contraction: the reference forms points = cam + z * dir as two torch ops, and the
+    // KNN selection downstream is sensitive to the last bit of the point
+    x = __fadd_rn(cam[3 * ray], __fmul_rn(t, dirs[3 * ray]));
+    y = __fadd_rn(cam[3 * ray + 1], __fmul_rn(t, dirs[3 * ray + 1]));
+    z = __fadd_rn(cam[3 * ray + 2], __fmul_rn(t, dirs[3 * ray + 2]));
   } else {
     x = xin[3 * gp], y = xin[3 * gp + 1], z = xin[3 * gp + 2];
   }

@@ -40,7 +40,8 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// exclusive scan of one value per lane
+// exclusive scan of one value per lane.  (Not inclusive - v: the last sample's free energy is 1e10 * sigma, and
+// subtracting it back would cancel the whole prefix.)
 __device__ __forceinline__ float warp_excl_scan(float v, int lane) {
   float x = v;
 #pragma unroll
@@ -48,7 +49,8 @@ __device__ __forceinline__ float warp_excl_scan(float v, int lane) {
     float y = __shfl_up_sync(0xffffffffu, x, o);
     if (lane >= o) x += y;
   }
-  return x - v;
+  float e = __shfl_up_sync(0xffffffffu, x, 1);
+  return lane == 0 ? 0.f : e;
 }
 
 // in-place bitonic sort (ascending) of n = power of two floats in shared memory by one warp, with payload

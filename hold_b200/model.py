@@ -50,7 +50,7 @@ class ImplicitNet(nn.Module):
         for l in range(9):
             out = dims[l + 1] - 39 if l + 1 == 4 else dims[l + 1]
             setattr(self, f"lin{l}", _wn_linear(dims[l] if l > 0 else d0, out))
-        self._node = None
+        object.__setattr__(self, "_node", None)
 
     def forward(self, x, cond=None):
         if x.ndim == 2:
@@ -174,7 +174,7 @@ class Node(nn.Module):
         self.kind = "hand" if node_id in ("right", "left") else "object"
         self.class_id = CLASS_ID[node_id]
         self.implicit_network = ImplicitNet(self.kind)
-        self.implicit_network._node = self
+        object.__setattr__(self.implicit_network, "_node", self)  # back-reference, not a submodule
         self.rendering_network = RenderingNet(self.kind)
         self.density = LaplaceDensity(beta)
         self.sampler_cfg = dict(sampler_cfg)
@@ -252,6 +252,7 @@ class ErrorBoundSampler:
 
     def get_z_vals(self, ray_dirs, cam_loc, pose: NodePose, B: int, rand=None):
         n = self.node
+        ray_dirs, cam_loc = ray_dirs.float().contiguous(), cam_loc.float().contiguous()
         R = ray_dirs.shape[0]
         z = torch.empty(R, n.S, device=ray_dirs.device)
         iters = torch.zeros(1, dtype=torch.int32, device=ray_dirs.device)

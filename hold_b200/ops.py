@@ -21,6 +21,7 @@ def camera_rays(ctx, uv, pose, intrinsics):
 def shade(node, ray_dirs, cam_loc, pose: NodePose, z_vals, B: int):
     R, S = z_vals.shape
     dev = z_vals.device
+    ray_dirs, cam_loc = ray_dirs.float().contiguous(), cam_loc.float().contiguous()
     t = dict(color=torch.empty(R, S, 3, device=dev), normal=torch.empty(R, S, 3, device=dev), density=torch.empty(R, S, device=dev),
              z_vals=z_vals.contiguous(), sdf=torch.empty(R, S, device=dev), canonical_pts=torch.empty(R, S, 3, device=dev))
     f = Factors()

@@ -430,12 +430,15 @@ def volumetric_render(f, is_training=False):
     return out
 
 
-def merge_factors(fl):
-    """hold/hold_utils.py:76-121: concat on the sample axis, sort by z, drop (n-1) head / n tail."""
+def merge_factors(fl, stable=False):
+    """hold/hold_utils.py:76-121: concat on the sample axis, sort by z, drop (n-1) head / n tail.
+    The reference calls torch.sort without stable=True, so the order of EXACT z ties between nodes (common: all
+    nodes share the ray's uniform grid, near and far) is implementation-defined (CPU introsort != CUDA segmented
+    sort).  `stable=True` fixes the canonical order hold_b200 implements (lower node first)."""
     n = len(fl)
     keys = ["color", "normal", "density", "semantics", "z_vals"]
     cat = {k: torch.cat([f[k] for f in fl], 1) for k in keys}
-    zs, ind = torch.sort(cat["z_vals"], dim=1)
+    zs, ind = torch.sort(cat["z_vals"], dim=1, stable=stable)
     out = {}
     for k in keys:
         if k == "z_vals":
@@ -514,9 +517,9 @@ def node_forward(kind, class_id, dirs, cam, frame_of_ray, sdf_sd, rgb_sd, beta_p
     }
 
 
-def composite(factors_list):
+def composite(factors_list, stable=False):
     """HOLDNet.forward_fg, hold/hold_net.py:76-88: composite render + per-node renders."""
-    comp = merge_factors(factors_list)
+    comp = merge_factors(factors_list, stable)
     out = {"comp": volumetric_render(comp)}
     out["comp"]["z_vals"] = comp["z_vals"]
     out["comp"]["indices"] = comp["indices"]
@@ -554,7 +557,7 @@ def scene_articulation(sc):
 CLASS_ID = {"object": 1, "right": 2, "left": 3}
 
 
-def render_scene(sc, ray_ids=None, chunk=None, trace=None):
+def render_scene(sc, ray_ids=None, chunk=None, trace=None, stable_ties=False):
     """Whole foreground path a1 -> a14 for the rays `ray_ids` (flat index into [B*H*W]) of a
     SynthScene, processed in calls of `chunk` rays (the reference renders 512-pixel chunks,
     datasets/eval_datasets.py:13; the sampler's convergence flag is per call, ray_sampler.py:244)."""
@@ -581,6 +584,6 @@ def render_scene(sc, ray_ids=None, chunk=None, trace=None):
                              time_code=sc.time_code if a["kind"] == "object" else None,
                              trace=None if trace is None else trace.setdefault(nid, []))
             fl.append(f)
-        comp = composite(fl)
+        comp = composite(fl, stable_ties)
         outs.append(dict(nodes=fl, render=comp))
     return outs, art
