@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — rays/s of the HOLD foreground hot path (SURVEY.md §8d metric) on N B200s.
+
+One "step" = one 512x512 frame (262 144 rays) of BASELINE.json configs[1] (right hand + rigid object,
+"128 samples/ray" = N_samples_eval 128 / N_samples 64 / N_samples_extra 32, density beta 0.03 so that the
+error-bound sampler runs all 5 rounds — the worst case) through hold_render_fg: rays -> 5 sampler rounds
+(inverse LBS + SDF net on 128 new samples/ray/round) -> shading of the 98 final samples (SDF + gradient +
+feature, skinning Jacobian, colour net, density) -> n-way merge + volume integration, for every node.
+
+  python bench.py --gpus N --steps K --warmup W            # ours (torchrun for N > 1)
+  python bench.py --impl reference [--steps K]             # the reference algorithm on the host CPU cores
+
+Rays shard over ranks with no data-path collective (render.py has no gradients): each rank renders
+its own frames -> "scaling": "weak".  Timing: CUDA events around exactly K steps, barrier + synchronize on
+both sides, max over ranks.  Every step's inputs are 3.3 GB of per-sample work (>> L2), so L2 is cold for the
+streamed data by construction; the weights (a few MB) are meant to be L2-resident.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 512
+S = 128
+BETA = 0.03
+NODES = ("right", "object")
+# algorithmic MACs: SDF net 524 544 / point, of which the sampler rounds need the sdf head only
+MAC_SDF_FULL = 39 * 256 + 2 * 256 * 256 + 256 * 217 + 4 * 256 * 256 + 256 * 257
+MAC_SDF_HEAD = MAC_SDF_FULL - 256 * 256          # no feature rows of lin8
+MAC_GRAD = 459_008                               # reverse-mode count of d sdf / d x
+MAC_RGB = {"right": 266_496, "left": 266_496, "object": 274_688}
+
+
+def flops_per_ray(rounds: int, nodes=NODES, n_eval=S, s_final=S // 2 + S // 4 + 2) -> float:
+    """F = r * N_eval * F_sdf + S_f * (F_sdf + F_grad + F_rgb), summed over nodes."""
+    tot = 0.0
+    for nid in nodes:
+        tot += rounds * n_eval * 2 * MAC_SDF_FULL + s_final * 2 * (MAC_SDF_FULL + MAC_GRAD + MAC_RGB[nid])
+    return tot
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_scene(seed=0, H_=H, W_=W):
+    from hold_b200 import synth
+
+    sc = synth.make_scene(H=H_, W=W_, S=S, nodes=NODES, B=1, seed=seed)
+    for nid in sc.node_ids:
+        sc.beta[nid] = torch.tensor(BETA)
+    return sc
+
+
+def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, threads: int | None = None):
+    """The reference's algorithm (oracle port, pinned to the reference modules by oracle/ref_harness.py) on the
+    host cores, in the reference's own 512-ray chunks (datasets/eval_datasets.py:13)."""
+    from oracle import hold_oracle as O
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sc2 = make_scene(0)
+    g = torch.Generator().manual_seed(11)
+    ids = torch.sort(torch.randperm(H * W, generator=g)[:n_rays]).values
+    O.render_scene(sc2, ray_ids=ids[:64], chunk=64)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        O.render_scene(sc2, ray_ids=ids, chunk=512)
+    dt = time.perf_counter() - t0
+    return n_rays * repeats / dt, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = 512
+    rps, threads, dt = cpu_reference_rays_per_s(n_rays, repeats=max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": "rays/sec (128 samples/ray)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: right hand + rigid object, 512x512 frame, 128 samples/ray (N_eval 128, N 64, extra 32), beta 0.03 -> 5 sampler rounds",
+                   "sample": f"{n_rays} rays of the frame per step, 512-ray chunks"},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_rays} rays x {max(1, args.steps)} steps of the 512x512 workload, torch CPU fp32, {threads} threads"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("HOLD_MLP_MODE", "auto"), choices=["auto", "fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import __graft_entry__ as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from hold_b200 import capi, scene_io
+
+    capi.lib()
+    ctx = capi.Context(local_rank)
+    use_tc = (args.mode == "tc") or (args.mode == "auto" and getattr(capi, "TC_READY", False))
+    mode = capi.MLP_TC if use_tc else capi.MLP_FP32
+    sc = make_scene(seed=0)           # every rank renders the same scene description; frames differ only by index
+    net = scene_io.build_net(sc, ctx, mode)
+    inp_host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in scene_io.scene_input(sc, torch.device("cpu")).items()}
+    inp_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp_host.items()}
+    R = H * W
+
+    def step_resident():
+        return net.forward_fg(inp_dev, return_factors=False, want_weights=False)
+
+    out_keys = ("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights")
+    host_out = {k: None for k in out_keys}
+
+    def step_e2e():
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in inp_host.items()}
+        o = net.forward_fg(d, return_factors=False, want_weights=False)
+        for k in out_keys:
+            host_out[k] = o[k].to("cpu", non_blocking=True)
+        return o
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        for _ in range(steps):
+            o = fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launches - l0, o
+
+    for _ in range(args.warmup):
+        o = step_resident()
+    torch.cuda.synchronize()
+    ctx.check()
+    iters = [int(x) for x in o["sampler_iters"].tolist()]
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, launches, o = timed(step_resident, args.steps)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if rank == 0:
+        clocks.stop_flag.set()
+        clocks.join(timeout=2)
+    value = world * R * args.steps / (ms * 1e-3)
+    e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in inp_host.values() if torch.is_tensor(v))
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values() if v is not None)
+
+    # ---- roofline of the dominant kernel: the SDF-net launch of one sampler round (R x 128 points), timed live
+    P = R * S
+    xc = (torch.rand(P, 3, device=dev) - 0.5) * 1.6
+    sdf = torch.empty(P, device=dev)
+    node = net.nodes["right"]
+    import ctypes as C
+
+    def sdf_launch():
+        capi.check(capi.lib().hold_sdf_eval(ctx.h, node.slot, P, capi.ptr(xc), None, capi.ptr(sdf), None, None, capi.stream_ptr()))
+
+    for _ in range(2):
+        sdf_launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_l = 5
+    e0.record()
+    for _ in range(n_l):
+        sdf_launch()
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / n_l
+    burst, sustained, how = measured_peaks()
+    k_flops = 2.0 * MAC_SDF_HEAD * P
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    passes = 3 if use_tc else 1
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+        "kernel": "SDF-net launch of one sampler round (262144 x 128 points, sdf head only: 0.918 MFLOP/point algorithmic)",
+        "ms_per_launch": k_ms, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, burst: kernel timed alone)",
+        "mma_mode": "tcgen05 kind::f16 bf16 x3 split (fp32-exact operands, fp32 accumulate)" if use_tc else "fp32 FFMA on CUDA cores (no tensor pipe)",
+        "frac_of_mode_peak": achieved / (burst / passes) if use_tc else None,
+        "whole_step_tflops": world * flops_per_ray(max(iters)) * R * args.steps / (ms * 1e-3) / 1e12,
+        "whole_step_frac_of_sustained": world * flops_per_ray(max(iters)) * R * args.steps / (ms * 1e-3) / 1e12 / (sustained * world),
+    }
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        rps, threads, dt = cpu_reference_rays_per_s(512, repeats=1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+               "sample": f"512 rays (one reference-sized chunk) of the same 512x512 workload in {dt:.1f} s; oracle/hold_oracle.py (torch CPU fp32)"}
+    line = {
+        "metric": "rays/sec (128 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: right hand + rigid object, 512x512 frame per step per GPU, 128 samples/ray (N_eval 128, N 64, extra 32), beta 0.03",
+                   "nodes": list(NODES), "rays_per_step_per_gpu": R, "sampler_rounds": iters, "parallelism": f"rays/frames sharded x{world}, no collective",
+                   "l2": "per-step working set 3.3 GB of samples >> 126 MB L2 (inputs larger than L2)",
+                   "mlp_mode": "tcgen05 bf16x3" if use_tc else "fp32 CUDA cores"},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -166,3 +166,4 @@ def mlp_weights(sd: dict, n_layers: int) -> tuple[MlpWeights, list]:
         w.weight_g[l] = g.data_ptr() if g is not None else None
         w.bias[l] = b.data_ptr()
     return w, keep
+TC_READY = True  # tcgen05 MLP path built into libhold_b200.so

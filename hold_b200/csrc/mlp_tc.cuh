@@ -1,13 +1,565 @@
-// tcgen05 (5th-gen tensor core) MLP path — HOLD_MLP_TC.  (placeholder: filled in below the fp32 path)
+// tcgen05 (5th-gen tensor core) fused MLP chains — HOLD_MLP_TC.
+//
+// One persistent CTA per SM walks 128-row tiles through the whole layer chain:
+//   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled bf16 weight chunks L2 -> smem ring
+//   * warp 1 (1 lane)  : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
+//   * warps 2..5       : epilogue — tcgen05.ld the accumulator in 64-column chunks, bias + activation in fp32,
+//                        split into bf16 hi/lo and write the next layer's A operand (SW128 K-major) to smem;
+//                        chunk-level mbarriers let layer l+1's MMAs start while layer l's epilogue is running.
+// Arithmetic: every fp32 operand x is split x = hi + lo (bf16 each) and each product is three MMAs
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate) — ~2^-16 relative per product, which is what the 1e-4 parity bar
+// needs; plain bf16 (2^-9) does not meet it (SURVEY §7 "hard parts").  The sdf / rgb heads (1 resp. 3 output
+// rows) are fp32 dot products in the epilogue.  Gradients: forward mode, 4 rows per point (see mlp_simt.cuh).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "mlp_simt.cuh"
+
 namespace hold {
-struct TcMlp { int dummy; };
-static int tc_init(hold_ctx*) { return HOLD_OK; }
-static void tc_free(NodeState&) {}
-static int tc_pack(hold_ctx*, NodeState&, const hold_mlp_weights*, const hold_mlp_weights*, cudaStream_t) { return HOLD_OK; }
-static int tc_launch_sdf(hold_ctx*, NodeState&, int, const float*, const float*, float*, float*, float*, const SamplerState*, cudaStream_t) {
-  set_error("HOLD_MLP_TC not built"); return HOLD_E_STATE; }
-static int tc_launch_rgb(hold_ctx*, NodeState&, int, int, const float*, const float*, const float*, const float*, const float*, float*, cudaStream_t) {
-  set_error("HOLD_MLP_TC not built"); return HOLD_E_STATE; }
+
+constexpr int kTcRows = 128;
+constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] bf16 hi (16 KB) + lo (16 KB)
+constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] bf16
+constexpr int kTcThreads = 192;
+
+struct TcLayer {
+  const uint8_t* wimg;  // pre-swizzled stage images, nst * 32 KB
+  const float* bias;    // [256]
+  int nst;              // number of 32-wide k stages
+  int N;                // valid outputs
+};
+
+struct TcMlp {
+  uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
+  uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
+  int sdf_nst[HOLD_MAX_LAYERS], rgb_nst[HOLD_MAX_LAYERS];
+};
+
+struct TcArgs {
+  int P, n_layers;
+  TcLayer L[HOLD_MAX_LAYERS];
+  const float* w_last;
+  const float* b_last;
+  const float* xc;
+  const float* embed_w;
+  float* sdf;
+  float* grad;
+  float* feat;
+  const float* normal;
+  const float* pose_embed;
+  const float* time_code;
+  int pts_per_frame, k0;
+  float* rgb;
+  const SamplerState* st;
+  int* err;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+  uint32_t done = 0;
+  for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  if (err != nullptr) atomicOr(err, 0x100 | (tag << 12));
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major canonical layouts (cute/arch/mma_sm100_desc.hpp semantics):
+// start address >> 4 | LBO (=1, unused for swizzled K-major) | SBO = bytes between 8-row groups | version 1 | layout
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// x = hi + lo (+ O(2^-17 x)): hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
+    __nv_bfloat162 hh;
+    hh.x = h0, hh.y = h1;
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = pack_bf16x2(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// byte offset of the 16-byte unit holding k = 8j..8j+7 of row r inside one [128 x 64] SW128 K-major A chunk
+__device__ __forceinline__ uint32_t a_unit_off(int r, int j) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ float softplus100_fast(float x, float& e_out) {
+  // Softplus(beta=100, threshold=20): x if 100x > 20 else log1p(exp(100x))/100, MUFU ex2/lg2
+  float bx = x * 100.0f;
+  float e = __expf(fminf(bx, 20.0f));
+  e_out = e;
+  float sp = __logf(1.0f + e) * 0.01f;
+  return (bx > 20.0f) ? x : sp;
+}
+
+template <int MODE>
+struct TcCfg {
+  static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;
+  static constexpr int kStages = (MODE == MLP_COLOR) ? 2 : 3;
+  static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
+  static constexpr int kSmemW = kStages * kTcStageBytes;
+  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers + 1 KB alignment slack
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
+  if (a.st != nullptr && a.st->done) return;
+  using Cfg = TcCfg<MODE>;
+  constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages;
+  constexpr int RPP = (MODE == MLP_SDF_JVP) ? 4 : 1;
+  constexpr int PPT = kTcRows / RPP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
+  const uint32_t sBar = sW + Cfg::kSmemW;
+  // barrier map (8 B each)
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NA;
+  const uint32_t sTmemPtr = bDFull + 16;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = ceil_div(a.P, PPT);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
+    for (int i = 0; i < NA; ++i) mbar_init(bAReady + 8 * i, 128);
+    mbar_init(bDFull, 1);
+    mbar_init(bDFull + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
+
+  if (warp == 0) {
+    // ============================================================ weight producer (TMA engine, bulk async copies)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < a.n_layers; ++l) {
+          const uint8_t* src = a.L[l].wimg;
+          for (int s = 0; s < a.L[l].nst; ++s) {
+            mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1);
+            mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
+            bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_par = 0;  // bit c = parity to wait for on a_ready[c]
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < a.n_layers; ++l) {
+          const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * 256);
+          const int nst = a.L[l].nst;
+          for (int s = 0; s < nst; ++s) {
+            const int c = s >> 1;  // A chunk (64 k) of this 32-k stage
+            if ((s & 1) == 0) {
+              mbar_wait(bAReady + 8 * c, (a_par >> c) & 1, a.err, 2);
+              a_par ^= (1u << c);
+              tc_fence_after();
+            }
+            mbar_wait(bWFull + 8 * stage, phase, a.err, 3);
+            tc_fence_after();
+            const uint32_t wb = sW + stage * kTcStageBytes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
+              const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+              const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+              const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
+              const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
+              tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
+              tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
+              tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
+            }
+            tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(bDFull + 8 * (l & 1));  // accumulator of layer l complete
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue warps (128 threads = 128 TMEM lanes)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* gA_hi = gen_base;
+    uint8_t* gA_lo = gen_base + NA * kTcAChunkBytes;
+    uint32_t d_par = 0;  // bit b = parity to wait for on d_full[b]
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int p = tile * PPT + row / RPP;
+      const int comp = row % RPP;
+      const bool valid = p < a.P;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      // ---------------------------------------------------------- prologue: layer-0 A operand
+      if (MODE != MLP_COLOR) {
+        if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
+        float e[64];
+        embed_row(e, px, py, pz, comp, a.embed_w, 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 hi, lo;
+          split8(e + 8 * j, hi, lo);
+          *reinterpret_cast<uint4*>(gA_hi + a_unit_off(row, j)) = hi;
+          *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, j)) = lo;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bAReady);
+      } else {
+        const int b = valid ? p / a.pts_per_frame : 0;
+        for (int c = 0; c < 5; ++c) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k = c * 64 + j * 8 + i;
+              float v = 0.f;
+              if (valid) {
+                if (k < kFeat) v = a.feat[(size_t)p * kFeat + k];
+                else {
+                  const int e = k - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
+                  if (e < 3) v = a.xc[3 * (size_t)p + e];
+                  else if (e < 6) v = a.normal[3 * (size_t)p + e - 3];
+                  else if (e < 14) v = (a.pose_embed != nullptr) ? a.pose_embed[b * 8 + e - 6] : 0.f;
+                  else if (e < a.k0 - kFeat) v = a.time_code[b * 32 + e - 14];
+                }
+              }
+              x[i] = v;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+            *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bAReady + 8 * c);
+        }
+      }
+      // ---------------------------------------------------------- per-layer epilogues
+      float head0 = 0.f, head1 = 0.f, head2 = 0.f;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const bool feat_layer = (MODE == MLP_SDF_JVP) && (l == a.n_layers - 1);
+        const bool head_layer = (MODE == MLP_COLOR) ? (l == a.n_layers - 1) : (l == 7);
+        const bool last_mma = (l == a.n_layers - 1);
+        const int N = a.L[l].N;
+        mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4);
+        d_par ^= (1u << (l & 1));
+        tc_fence_after();
+        const float* bias = a.L[l].bias;
+        const bool is_value = (comp == 0);
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int hblk = 0; hblk < 2; ++hblk) {
+            uint32_t raw[32];
+            tc_ld32(t_lane + (uint32_t)((l & 1) * 256 + c * 64 + hblk * 32), raw);
+            tc_wait_ld();
+            float out[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = c * 64 + hblk * 32 + i;
+              float z = __uint_as_float(raw[i]);
+              if (is_value) z += __ldg(bias + n);
+              float o;
+              if (MODE == MLP_COLOR) {
+                o = fmaxf(z, 0.f);
+              } else if (feat_layer) {
+                o = z;
+              } else {
+                float e;
+                float sp = softplus100_fast(z, e);
+                if (MODE == MLP_SDF_JVP) {
+                  // softplus'(z) = e/(1+e) of the VALUE row (lane & ~3), applied to the tangent rows
+                  float s = (z * 100.0f > 20.0f) ? 1.0f : __fdividef(e, 1.0f + e);
+                  float sv = __shfl_sync(0xffffffffu, s, lane & ~3);
+                  o = is_value ? sp : z * sv;
+                } else {
+                  o = sp;
+                }
+                if (n >= N) {  // skip connection: embedding columns of layer 3's output (shape_net.py:121-122)
+                  const int ei = n - N;
+                  float ev = 0.f;
+                  if (ei < kEmbed) {
+                    const int d = ei % 3;
+                    const float pc = (d == 0) ? px : ((d == 1) ? py : pz);
+                    if (ei < 3) ev = (comp == 0) ? pc : ((comp - 1 == d) ? 1.f : 0.f);
+                    else {
+                      const int qq = (ei - 3) / 3;
+                      const float f = (float)(1 << (qq >> 1));
+                      const float arg = pc * f;
+                      if (comp == 0) ev = (qq & 1) ? cosf(arg) : sinf(arg);
+                      else ev = (comp - 1 == d) ? ((qq & 1) ? -f * sinf(arg) : f * cosf(arg)) : 0.f;
+                    }
+                    if (a.embed_w != nullptr) ev *= a.embed_w[ei];
+                  }
+                  o = ev;
+                }
+              }
+              out[i] = o;
+              if (head_layer) {
+                if (MODE == MLP_COLOR) {
+                  head0 += o * __ldg(a.w_last + n);
+                  head1 += o * __ldg(a.w_last + 256 + n);
+                  head2 += o * __ldg(a.w_last + 512 + n);
+                } else {
+                  head0 += o * __ldg(a.w_last + n);
+                }
+              }
+            }
+            if (feat_layer) {
+              if (valid && is_value) {
+                float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + c * 64 + hblk * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+              }
+            } else if (!last_mma) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                uint4 hi, lo;
+                split8(out + 8 * jj, hi, lo);
+                const int j = hblk * 4 + jj;
+                *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+                *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+              }
+            }
+          }
+          if (!last_mma) {
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bAReady + 8 * c);
+          }
+        }
+        if (head_layer) {
+          if (MODE == MLP_COLOR) {
+            if (valid) {
+              a.rgb[3 * (size_t)p] = 1.0f / (1.0f + __expf(-(head0 + a.b_last[0])));
+              a.rgb[3 * (size_t)p + 1] = 1.0f / (1.0f + __expf(-(head1 + a.b_last[1])));
+              a.rgb[3 * (size_t)p + 2] = 1.0f / (1.0f + __expf(-(head2 + a.b_last[2])));
+            }
+          } else if (valid) {
+            if (comp == 0) a.sdf[p] = head0 + a.b_last[0];
+            else a.grad[3 * (size_t)p + comp - 1] = head0;
+          }
+        }
+      }
+      tc_fence_before();  // all TMEM reads of this tile precede the next tile's first MMA (ordered by a_ready)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// One stage image = [256 n x 32 k] bf16 in the SW64 K-major canonical layout, hi part then lo part.
+// W[n][k] = scale * fold(v, g)[row_off + n][colmap(k)];  colmap: k -> source column (or -1 => 0).
+__global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N, int K,
+                          int kpad, float scale, int perm_feat_first, uint8_t* __restrict__ img) {
+  const int n = blockIdx.x;  // 0..255
+  __shared__ float red[32];
+  __shared__ float f_sh;
+  float f = 0.f;
+  const float* vr = v + (size_t)(row_off + (n < N ? n : 0)) * in_dim;
+  if (g != nullptr) {
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < in_dim; k += blockDim.x) ss += vr[k] * vr[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < blockDim.x / 32; ++w) tot += red[w];
+      f_sh = g[row_off + (n < N ? n : 0)] / sqrtf(tot);
+    }
+    __syncthreads();
+    f = f_sh;
+  } else {
+    f = 1.0f;
+  }
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    int src = k;
+    if (perm_feat_first) {  // colour lin0: A order [feat(256) | x_c, n, pose(14) | time(32)] vs weight order [14 | 256 | 32]
+      if (k < kFeat) src = 14 + k;
+      else if (k < kFeat + 14) src = k - kFeat;
+      else src = k;
+    }
+    float w = (n < N && src < K) ? scale * (vr[src] * f) : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(w);
+    __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const int st = k >> 5, kk = k & 31;
+    const size_t off = (size_t)st * kTcStageBytes + (size_t)((n >> 3) * 512 + (n & 7) * 64 + ((((kk >> 3) ^ ((n >> 1) & 3))) << 4) + (kk & 7) * 2);
+    *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(img + off + 16384) = l;
+  }
+}
+
+static int tc_init(hold_ctx*) {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_JVP>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
+  if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
+  return HOLD_OK;
+}
+
+static void tc_free(NodeState& ns) {
+  if (!ns.tc) return;
+  for (int l = 0; l < HOLD_MAX_LAYERS; ++l) {
+    if (ns.tc->sdf_img[l]) cudaFree(ns.tc->sdf_img[l]);
+    if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
+  }
+  delete ns.tc;
+  ns.tc = nullptr;
+}
+
+static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, cudaStream_t s) {
+  if (!ns.tc) ns.tc = new TcMlp();
+  TcMlp& t = *ns.tc;
+  for (int l = 0; l < 9; ++l) {
+    const int K = (l == 0) ? kEmbed : kHidden, kpad = (l == 0) ? 64 : 256;
+    const int N = (l == 3) ? kHidden - kEmbed : kHidden;
+    const int row_off = (l == 8) ? 1 : 0;
+    t.sdf_nst[l] = kpad / 32;
+    if (!t.sdf_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_img[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
+    const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
+    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  for (int l = 0; l < 4; ++l) {
+    const int K = (l == 0) ? rgb->in_dim[0] : 256, kpad = (l == 0) ? 320 : 256;
+    t.rgb_nst[l] = kpad / 32;
+    if (!t.rgb_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img[l], (size_t)t.rgb_nst[l] * kTcStageBytes));
+    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 1 : 0, t.rgb_img[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  return HOLD_OK;
+}
+
+static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, const float* embed_w, float* sdf, float* grad,
+                         float* feat, const SamplerState* st, cudaStream_t s) {
+  const bool jvp = (grad != nullptr) || (feat != nullptr);
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = P, a.n_layers = jvp ? 9 : 8;
+  for (int l = 0; l < a.n_layers; ++l) {
+    a.L[l].wimg = ns.tc->sdf_img[l], a.L[l].bias = ns.sdf.bias[l], a.L[l].nst = ns.tc->sdf_nst[l], a.L[l].N = ns.sdf.N[l];
+  }
+  a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
+  a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
+  if (jvp) {
+    HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
+    int tiles = ceil_div(P, kTcRows / 4);
+    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
+  } else {
+    int tiles = ceil_div(P, kTcRows);
+    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+  }
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame, const float* xc, const float* normal,
+                         const float* pe, const float* feat, const float* time_code, float* rgb, cudaStream_t s) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = P, a.n_layers = 4;
+  for (int l = 0; l < 4; ++l) {
+    a.L[l].wimg = ns.tc->rgb_img[l], a.L[l].bias = ns.rgb.bias[l], a.L[l].nst = ns.tc->rgb_nst[l], a.L[l].N = 256;
+  }
+  a.w_last = ns.rgb.w_last, a.b_last = ns.rgb.b_last;
+  a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
+  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err;
+  int tiles = ceil_div(P, kTcRows);
+  k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+}  // namespace hold
