@@ -1,17 +1,20 @@
 // tcgen05 (5th-gen tensor core) fused MLP chains — HOLD_MLP_TC.
 //
 // One persistent CTA per SM walks 128-row tiles through the whole layer chain:
-//   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled bf16 weight chunks L2 -> smem ring
+//   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled fp16 weight chunks L2 -> smem ring
 //   * warp 1 (1 lane)  : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
 //   * warps 2..5       : epilogue — tcgen05.ld the accumulator in 64-column chunks, bias + activation in fp32,
-//                        split into bf16 hi/lo and write the next layer's A operand (SW128 K-major) to smem;
+//                        split into fp16 hi/lo and write the next layer's A operand (SW128 K-major) to smem;
 //                        chunk-level mbarriers let layer l+1's MMAs start while layer l's epilogue is running.
-// Arithmetic: every fp32 operand x is split x = hi + lo (bf16 each) and each product is three MMAs
-// (hi*hi + lo*hi + hi*lo, fp32 accumulate) — ~2^-16 relative per product, which is what the 1e-4 parity bar
-// needs; plain bf16 (2^-9) does not meet it (SURVEY §7 "hard parts").  The sdf / rgb heads (1 resp. 3 output
+// Arithmetic: every fp32 operand x is split x = hi + lo (fp16 each: 11 + 11 mantissa bits) and each product is
+// three MMAs (hi*hi + lo*hi + hi*lo, fp32 accumulate) — ~2^-21 relative per product (measured 2.5e-7 on a
+// 256-term dot, i.e. fp32-GEMM level), with an absolute floor of ~3e-8 where lo goes subnormal.  This is what the
+// 1e-4 parity bar needs: an sdf error eps reaches the density as eps/beta^2 (beta down to 1e-2), so plain bf16
+// (2^-9) and even a bf16 split (2^-16, measured 83 % of pixels within 1e-4) do not meet it (SURVEY §7 "hard
+// parts").  Range: |x| must stay below 65504 (activations/weights here are O(1e-3..1e2)).  The sdf / rgb heads (1 resp. 3 output
 // rows) are fp32 dot products in the epilogue.  Gradients: forward mode, 4 rows per point (see mlp_simt.cuh).
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "mlp_simt.cuh"
@@ -22,6 +25,11 @@ constexpr int kTcRows = 128;
 constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] bf16 hi (16 KB) + lo (16 KB)
 constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] bf16
 constexpr int kTcThreads = 192;
+// Power-of-two operand scaling (exact): fp16 operands are fed to the tensor core as A * 2^6 and W * 2^10 so that
+// the LOW halves of the hi/lo split stay in fp16's normal range for |a| >= 2e-3, |w| >= 1.2e-4 (unscaled, the low
+// half of every |x| < 0.125 is subnormal; measured: the split then gains only 2x over bf16).  The accumulator is
+// rescaled by 2^-16 in the epilogue's bias FMA.  Range: |a| < 1023, |w| < 64.
+constexpr float kTcScaleA = 64.0f, kTcScaleW = 1024.0f, kTcUnscale = 1.0f / (64.0f * 1024.0f);
 
 struct TcLayer {
   const uint8_t* wimg;  // pre-swizzled stage images, nst * 32 KB
@@ -127,24 +135,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=128
+constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// x = hi + lo (+ O(2^-17 x)): hi = bf16(x), lo = bf16(x - hi)
+// x = hi + lo: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
-    __nv_bfloat162 hh;
-    hh.x = h0, hh.y = h1;
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
-    l[i] = pack_bf16x2(r0, r1);
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -155,13 +158,51 @@ __device__ __forceinline__ uint32_t a_unit_off(int r, int j) {
 }
 
 __device__ __forceinline__ float softplus100_fast(float x, float& e_out) {
-  // Softplus(beta=100, threshold=20): x if 100x > 20 else log1p(exp(100x))/100, MUFU ex2/lg2
+  // kTcScaleA * Softplus(beta=100, threshold=20)(x): x if 100x > 20 else log1p(exp(100x))/100, MUFU ex2/lg2
   float bx = x * 100.0f;
   float e = __expf(fminf(bx, 20.0f));
   e_out = e;
-  float sp = __logf(1.0f + e) * 0.01f;
-  return (bx > 20.0f) ? x : sp;
+  float sp = __logf(1.0f + e) * (0.01f * kTcScaleA);
+  return (bx > 20.0f) ? x * kTcScaleA : sp;
 }
+
+// One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
+// w.r.t. coordinate comp-1.  Deliberately NOT inlined: it is called from rolled loops at the tile prologue and
+// at the skip layer, and inlining 39 sinf/cosf bodies would blow the instruction cache of the hot epilogue.
+__device__ __noinline__ float embed_val(int e, int comp, float px, float py, float pz, const float* __restrict__ ew) {
+  if (e >= kEmbed) return 0.f;
+  const int d = e % 3;
+  const float pc = (d == 0) ? px : ((d == 1) ? py : pz);
+  float v;
+  if (e < 3) {
+    v = (comp == 0) ? pc : ((comp - 1 == d) ? 1.f : 0.f);
+  } else {
+    const int qq = (e - 3) / 3;
+    const float f = (float)(1 << (qq >> 1));
+    const float arg = pc * f;
+    if (comp == 0) v = (qq & 1) ? cosf(arg) : sinf(arg);
+    else v = (comp - 1 == d) ? ((qq & 1) ? -f * sinf(arg) : f * cosf(arg)) : 0.f;
+  }
+  if (ew != nullptr) v *= ew[e];
+  return v;
+}
+
+constexpr int kTcW = 4;                        // epilogue warps per TMEM lane quarter
+constexpr int kTcCW = 64 / kTcW;               // accumulator columns per warp per 64-column chunk
+constexpr int kTcEpiWarps = 4 * kTcW;
+constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
+constexpr int kTcThreadsTotal = 64 + kTcEpiThreads;
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 
 template <int MODE>
 struct TcCfg {
@@ -173,17 +214,17 @@ struct TcCfg {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
+__global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages;
   constexpr int RPP = (MODE == MLP_SDF_JVP) ? 4 : 1;
   constexpr int PPT = kTcRows / RPP;
+  constexpr int CW = kTcCW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
   const uint32_t sBar = sW + Cfg::kSmemW;
-  // barrier map (8 B each)
   const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NA;
   const uint32_t sTmemPtr = bDFull + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
@@ -192,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
-    for (int i = 0; i < NA; ++i) mbar_init(bAReady + 8 * i, 128);
+    for (int i = 0; i < NA; ++i) mbar_init(bAReady + 8 * i, kTcEpiThreads);
     mbar_init(bDFull, 1);
     mbar_init(bDFull + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -260,27 +301,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
       }
     }
   } else {
-    // ============================================================ epilogue warps (128 threads = 128 TMEM lanes)
+    // ============================================================ epilogue: kTcW warps per TMEM lane quarter; warp
+    // `sub` of a quarter owns columns [sub*CW, (sub+1)*CW) of every 64-column chunk, so chunks complete in order
+    // and layer l+1's MMAs on chunk c start while chunks c+1.. of layer l are still in the epilogue.
     const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint8_t* gA_hi = gen_base;
     uint8_t* gA_lo = gen_base + NA * kTcAChunkBytes;
+    float* scratch = reinterpret_cast<float*>(gen_base);  // head partial sums (A region, free at tile end)
+    const int comp = row % RPP;
+    const bool is_value = (comp == 0);
     uint32_t d_par = 0;  // bit b = parity to wait for on d_full[b]
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int p = tile * PPT + row / RPP;
-      const int comp = row % RPP;
       const bool valid = p < a.P;
       float px = 0.f, py = 0.f, pz = 0.f;
-      // ---------------------------------------------------------- prologue: layer-0 A operand
+      // ---------------------------------------------------------- prologue: layer-0 A operand (this warp's columns)
       if (MODE != MLP_COLOR) {
         if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
-        float e[64];
-        embed_row(e, px, py, pz, comp, a.embed_w, 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int jj = 0; jj < CW / 8; ++jj) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(sub * CW + jj * 8 + i, comp, px, py, pz, a.embed_w);
           uint4 hi, lo;
-          split8(e + 8 * j, hi, lo);
+          split8(x, hi, lo);
+          const int j = sub * (CW / 8) + jj;
           *reinterpret_cast<uint4*>(gA_hi + a_unit_off(row, j)) = hi;
           *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, j)) = lo;
         }
@@ -291,26 +339,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
         const int b = valid ? p / a.pts_per_frame : 0;
         for (int c = 0; c < 5; ++c) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int jj = 0; jj < CW / 8; ++jj) {
             float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int k = c * 64 + j * 8 + i;
-              float v = 0.f;
+            const int k0 = c * 64 + sub * CW + jj * 8;
+            if (c < 4) {
               if (valid) {
-                if (k < kFeat) v = a.feat[(size_t)p * kFeat + k];
-                else {
-                  const int e = k - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
+                const float4 f0 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0);
+                const float4 f1 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0 + 4);
+                x[0] = f0.x, x[1] = f0.y, x[2] = f0.z, x[3] = f0.w, x[4] = f1.x, x[5] = f1.y, x[6] = f1.z, x[7] = f1.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
+                float v = 0.f;
+                if (valid) {
                   if (e < 3) v = a.xc[3 * (size_t)p + e];
                   else if (e < 6) v = a.normal[3 * (size_t)p + e - 3];
                   else if (e < 14) v = (a.pose_embed != nullptr) ? a.pose_embed[b * 8 + e - 6] : 0.f;
                   else if (e < a.k0 - kFeat) v = a.time_code[b * 32 + e - 14];
                 }
+                x[i] = v;
               }
-              x[i] = v;
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] *= kTcScaleA;
             uint4 hi, lo;
             split8(x, hi, lo);
+            const int j = sub * (CW / 8) + jj;
             *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
             *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
           }
@@ -330,102 +389,109 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(TcArgs a) {
         d_par ^= (1u << (l & 1));
         tc_fence_after();
         const float* bias = a.L[l].bias;
-        const bool is_value = (comp == 0);
         for (int c = 0; c < 4; ++c) {
+          const int n0 = c * 64 + sub * CW;
+          uint32_t raw[CW];
+          tc_ld16(t_lane + (uint32_t)((l & 1) * 256 + n0), raw);
+          float bv[CW];
 #pragma unroll
-          for (int hblk = 0; hblk < 2; ++hblk) {
-            uint32_t raw[32];
-            tc_ld32(t_lane + (uint32_t)((l & 1) * 256 + c * 64 + hblk * 32), raw);
-            tc_wait_ld();
-            float out[32];
+          for (int i = 0; i < CW / 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+            bv[4 * i] = b4.x, bv[4 * i + 1] = b4.y, bv[4 * i + 2] = b4.z, bv[4 * i + 3] = b4.w;
+          }
+          tc_wait_ld();
+          float out[CW];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = c * 64 + hblk * 32 + i;
-              float z = __uint_as_float(raw[i]);
-              if (is_value) z += __ldg(bias + n);
-              float o;
-              if (MODE == MLP_COLOR) {
-                o = fmaxf(z, 0.f);
-              } else if (feat_layer) {
-                o = z;
+          for (int i = 0; i < CW; ++i) {
+            // accumulator -> pre-activation (undo the operand scaling, add the bias on value rows); out[] holds the
+            // next layer's operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
+            const float z = fmaf(__uint_as_float(raw[i]), kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
+            float o;
+            if (MODE == MLP_COLOR) {
+              o = fmaxf(z, 0.f) * kTcScaleA;
+            } else if (feat_layer) {
+              o = z;
+            } else {
+              float e;
+              const float sp = softplus100_fast(z, e);
+              if (MODE == MLP_SDF_JVP) {
+                // softplus'(z) = e/(1+e) of the VALUE row (lane & ~3), applied to the tangent rows
+                const float s = (z * 100.0f > 20.0f) ? kTcScaleA : __fdividef(e * kTcScaleA, 1.0f + e);
+                const float sv = __shfl_sync(0xffffffffu, s, lane & ~3);
+                o = is_value ? sp : z * sv;
               } else {
-                float e;
-                float sp = softplus100_fast(z, e);
-                if (MODE == MLP_SDF_JVP) {
-                  // softplus'(z) = e/(1+e) of the VALUE row (lane & ~3), applied to the tangent rows
-                  float s = (z * 100.0f > 20.0f) ? 1.0f : __fdividef(e, 1.0f + e);
-                  float sv = __shfl_sync(0xffffffffu, s, lane & ~3);
-                  o = is_value ? sp : z * sv;
-                } else {
-                  o = sp;
-                }
-                if (n >= N) {  // skip connection: embedding columns of layer 3's output (shape_net.py:121-122)
-                  const int ei = n - N;
-                  float ev = 0.f;
-                  if (ei < kEmbed) {
-                    const int d = ei % 3;
-                    const float pc = (d == 0) ? px : ((d == 1) ? py : pz);
-                    if (ei < 3) ev = (comp == 0) ? pc : ((comp - 1 == d) ? 1.f : 0.f);
-                    else {
-                      const int qq = (ei - 3) / 3;
-                      const float f = (float)(1 << (qq >> 1));
-                      const float arg = pc * f;
-                      if (comp == 0) ev = (qq & 1) ? cosf(arg) : sinf(arg);
-                      else ev = (comp - 1 == d) ? ((qq & 1) ? -f * sinf(arg) : f * cosf(arg)) : 0.f;
-                    }
-                    if (a.embed_w != nullptr) ev *= a.embed_w[ei];
-                  }
-                  o = ev;
-                }
-              }
-              out[i] = o;
-              if (head_layer) {
-                if (MODE == MLP_COLOR) {
-                  head0 += o * __ldg(a.w_last + n);
-                  head1 += o * __ldg(a.w_last + 256 + n);
-                  head2 += o * __ldg(a.w_last + 512 + n);
-                } else {
-                  head0 += o * __ldg(a.w_last + n);
-                }
+                o = sp;
               }
             }
-            if (feat_layer) {
-              if (valid && is_value) {
-                float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + c * 64 + hblk * 32);
+            out[i] = o;
+          }
+          if (MODE != MLP_COLOR && n0 + CW > N) {  // skip connection: embedding columns of layer 3's output
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
-              }
-            } else if (!last_mma) {
+            for (int i = 0; i < CW; ++i)
+              if (n0 + i >= N) out[i] = kTcScaleA * embed_val(n0 + i - N, comp, px, py, pz, a.embed_w);
+          }
+          if (head_layer) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                uint4 hi, lo;
-                split8(out + 8 * jj, hi, lo);
-                const int j = hblk * 4 + jj;
-                *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
-                *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+            for (int i = 0; i < CW / 4; ++i) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
+              head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
+              if (MODE == MLP_COLOR) {
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + 256 + n0) + i);
+                const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.w_last + 512 + n0) + i);
+                head1 += out[4 * i] * w1.x + out[4 * i + 1] * w1.y + out[4 * i + 2] * w1.z + out[4 * i + 3] * w1.w;
+                head2 += out[4 * i] * w2.x + out[4 * i + 1] * w2.y + out[4 * i + 2] * w2.z + out[4 * i + 3] * w2.w;
               }
             }
           }
-          if (!last_mma) {
+          if (feat_layer) {
+            if (valid && is_value) {
+              float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
+#pragma unroll
+              for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+            }
+          } else if (!last_mma) {
+#pragma unroll
+            for (int jj = 0; jj < CW / 8; ++jj) {
+              uint4 hi, lo;
+              split8(out + 8 * jj, hi, lo);
+              const int j = sub * (CW / 8) + jj;
+              *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+              *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+            }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bAReady + 8 * c);
           }
         }
-        if (head_layer) {
-          if (MODE == MLP_COLOR) {
-            if (valid) {
-              a.rgb[3 * (size_t)p] = 1.0f / (1.0f + __expf(-(head0 + a.b_last[0])));
-              a.rgb[3 * (size_t)p + 1] = 1.0f / (1.0f + __expf(-(head1 + a.b_last[1])));
-              a.rgb[3 * (size_t)p + 2] = 1.0f / (1.0f + __expf(-(head2 + a.b_last[2])));
-            }
-          } else if (valid) {
-            if (comp == 0) a.sdf[p] = head0 + a.b_last[0];
-            else a.grad[3 * (size_t)p + comp - 1] = head0;
-          }
+      }
+      // ---------------------------------------------------------- heads: fixed-order reduction over the quarter's warps
+      // (all MMAs of the tile have completed, so the A region is free to hold the partial sums)
+      tc_fence_before();
+      constexpr int NH = (MODE == MLP_COLOR) ? 3 : 1;
+      scratch[(sub * NH + 0) * kTcRows + row] = head0;
+      if (MODE == MLP_COLOR) {
+        scratch[(sub * NH + 1) * kTcRows + row] = head1;
+        scratch[(sub * NH + 2) * kTcRows + row] = head2;
+      }
+      epi_bar();
+      if (sub == 0 && valid) {
+        float h[NH];
+#pragma unroll
+        for (int k = 0; k < NH; ++k) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w = 0; w < kTcW; ++w) acc += scratch[(w * NH + k) * kTcRows + row];
+          h[k] = acc * (1.0f / kTcScaleA);  // the head saw activations times kTcScaleA
+        }
+        if (MODE == MLP_COLOR) {
+#pragma unroll
+          for (int k = 0; k < NH; ++k) a.rgb[3 * (size_t)p + k] = 1.0f / (1.0f + __expf(-(h[k] + a.b_last[k])));
+        } else {
+          if (comp == 0) a.sdf[p] = h[0] + a.b_last[0];
+          else a.grad[3 * (size_t)p + comp - 1] = h[0];
         }
       }
-      tc_fence_before();  // all TMEM reads of this tile precede the next tile's first MMA (ordered by a_ready)
+      epi_bar();  // scratch is overwritten by the next tile's prologue
     }
   }
   tc_fence_before();
@@ -470,13 +536,13 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
       else if (k < kFeat + 14) src = k - kFeat;
       else src = k;
     }
-    float w = (n < N && src < K) ? scale * (vr[src] * f) : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(w);
-    __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    float w = (n < N && src < K) ? kTcScaleW * (scale * (vr[src] * f)) : 0.f;
+    __half h = __float2half_rn(w);
+    __half l = __float2half_rn(w - __half2float(h));
     const int st = k >> 5, kk = k & 31;
     const size_t off = (size_t)st * kTcStageBytes + (size_t)((n >> 3) * 512 + (n & 7) * 64 + ((((kk >> 3) ^ ((n >> 1) & 3))) << 4) + (kk & 7) * 2);
-    *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(img + off + 16384) = l;
+    *reinterpret_cast<__half*>(img + off) = h;
+    *reinterpret_cast<__half*>(img + off + 16384) = l;
   }
 }
 
@@ -536,10 +602,10 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   if (jvp) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     int tiles = ceil_div(P, kTcRows / 4);
-    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
   } else {
     int tiles = ceil_div(P, kTcRows);
-    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
@@ -557,7 +623,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
   a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err;
   int tiles = ceil_div(P, kTcRows);
-  k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreads, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
+  k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

