@@ -122,6 +122,14 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
     HOLD_REQUIRE(pose->posed_verts != nullptr, "hand node needs posed_verts");
     if (!ns.has_rig) { set_error("hand node has no rig (hold_node_set_rig)"); return HOLD_E_STATE; }
   }
+  if (hand && from_z && knn_idx == nullptr && outlier == nullptr) {
+    // hot path: consecutive samples of a ray per thread, KNN seeded from the previous sample
+    const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
+    dim3 g2(ceil_div(rays * segs, 128), B);
+    k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
+    HOLD_LAUNCH_CHECK(ctx);
+    return HOLD_OK;
+  }
 #define IW(H, Z) k_inverse_warp<H, Z><<<grid, 128, 0, s>>>(pts_per_frame, nsamp, zstride, zbuf, cam, dirs, xin, pose->tfs, \
                                                           pose->posed_verts, ns.skin_w, xc, knn_idx, outlier, st, ctx->dev_err)
   if (hand && from_z) IW(true, true);

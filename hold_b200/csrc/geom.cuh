@@ -58,6 +58,55 @@ __device__ __forceinline__ void knn15(const float* __restrict__ sv /*smem [778*3
   }
 }
 
+// Same result as knn15 for a point whose neighbour set is probably close to `r`'s current one (the previous sample
+// on the same ray): re-rank the 15 previous neighbours for the new point, which gives a tight upper bound on the
+// 15th distance at once, then scan all vertices — almost every vertex now fails the `dist < worst` test, so the
+// divergent insertion path that dominates knn15 (every warp takes it for most vertices) becomes rare.
+__device__ __forceinline__ void knn15_seeded(const float* __restrict__ sv, float px, float py, float pz, Knn15& r) {
+  int seed[kKnn];
+#pragma unroll
+  for (int k = 0; k < kKnn; ++k) { seed[k] = r.i[k]; r.d[k] = 3.0e38f; }
+#pragma unroll
+  for (int s = 0; s < kKnn; ++s) {
+    const int v = seed[s];
+    float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
+    float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // sorted insert by (dist, index): the final order must equal a full scan's (ties -> lower index first)
+    r.d[kKnn - 1] = dist;
+    r.i[kKnn - 1] = v;
+#pragma unroll
+    for (int k = kKnn - 1; k > 0; --k) {
+      bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
+      if (sw) {
+        float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
+        int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
+      }
+    }
+  }
+  for (int v = 0; v < kVerts; ++v) {
+    float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
+    float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    // candidate iff it would precede the current 15th entry in (dist, index) order
+    if (dist < r.d[kKnn - 1] || (dist == r.d[kKnn - 1] && v < r.i[kKnn - 1])) {
+      bool present = false;
+#pragma unroll
+      for (int k = 0; k < kKnn; ++k) present |= (r.i[k] == v);
+      if (!present) {
+        r.d[kKnn - 1] = dist;
+        r.i[kKnn - 1] = v;
+#pragma unroll
+        for (int k = kKnn - 1; k > 0; --k) {
+          bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
+          if (sw) {
+            float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
+            int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+}
+
 // query_skinning_weights_multi (model/mano/deformer.py:84-105) + blend of the 16 bone transforms
 // (`einsum("bpn,bnij->bpij")`, deformer.py:165): returns the top three rows of T = sum_j w_j tfs_j and
 // s = sum_j w_j tfs_j[3][3] (== sum of weights).
@@ -182,6 +231,47 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
     oz = sinv[8] * x + sinv[9] * y + sinv[10] * z + sinv[11];
   }
   xc[3 * gp] = ox, xc[3 * gp + 1] = oy, xc[3 * gp + 2] = oz;
+}
+
+// Hand-node variant of k_inverse_warp<true, true> that walks `kSeg` consecutive samples of one ray per thread and
+// seeds each sample's KNN from the previous one (knn15_seeded).  Same arithmetic, same results.
+constexpr int kSeg = 16;
+__global__ void __launch_bounds__(128)
+k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
+                         const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
+                         const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
+                         const SamplerState* __restrict__ st) {
+  if (st != nullptr && st->done) return;
+  __shared__ float sv[kVerts * 3];
+  __shared__ float stf[kJoints * 16];
+  const int b = blockIdx.y;
+  for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
+  for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
+  __syncthreads();
+  const int segs = (ns + kSeg - 1) / kSeg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rays_per_frame * segs) return;
+  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
+  const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
+  const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+  Knn15 nn;
+  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
+  for (int k = k0; k < k1; ++k) {
+    const float tz = zbuf[ray * zstride + k];
+    const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
+    if (k == k0) knn15(sv, x, y, z, nn);
+    else knn15_seeded(sv, x, y, z, nn);
+    float T[12], s, dmin;
+    blend_tf(nn, skin_w, stf, T, s, dmin);
+    float Ai[9];
+    inv3(T, 4, Ai);
+    const float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
+    const size_t gp = ray * ns + k;
+    xc[3 * gp] = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
+    xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
+    xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
+  }
 }
 
 // extract_features' normal (engine/volsdf_utils.py:66-102): J = d x_d / d x_c of forward skinning with detached

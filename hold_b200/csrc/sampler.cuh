@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(128) k_sampler_merge_beta(SamplerArgs a, int i
   float e0 = error_bound(m, n, beta0, lane);
   if (e0 <= a.eps) beta = beta0;
   float bmin = beta0, bmax = beta;
-  for (int j = 0; j < a.beta_iters; ++j) {
+  // A ray whose bound already holds at beta0 keeps beta0 through the line search (mid == beta0 every step), so
+  // the 10 extra evaluations are skipped for it — the result is bit-identical (ray_sampler.py:211-219).
+  const int n_bis = (e0 <= a.eps) ? 0 : a.beta_iters;
+  for (int j = 0; j < n_bis; ++j) {
     float mid = (bmin + bmax) / 2.0f;
     float e = error_bound(m, n, mid, lane);
     if (e <= a.eps) bmax = mid;

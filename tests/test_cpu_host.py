@@ -1,0 +1,92 @@
+"""CPU-only host logic: synthetic scenes are deterministic, the mirror modules keep the reference's state_dict key
+format, the FLOP accounting matches SURVEY §8d, and ray sharding (world_size 2, gloo) partitions the rays exactly."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_is_deterministic():
+    from hold_b200 import synth
+
+    a, b = synth.make_scene(H=8, W=8, S=32, seed=5), synth.make_scene(H=8, W=8, S=32, seed=5)
+    assert torch.equal(a.uv, b.uv) and torch.equal(a.mano["right"]["v_template"], b.mano["right"]["v_template"])
+    for k in a.sdf_state["right"]:
+        assert torch.equal(a.sdf_state["right"][k], b.sdf_state["right"][k])
+    m = a.mano["right"]
+    assert m["v_template"].shape == (778, 3) and m["shapedirs"].shape == (778, 3, 10) and m["posedirs"].shape == (135, 2334)
+    assert torch.allclose(m["lbs_weights"].sum(1), torch.ones(778), atol=1e-6)
+    assert torch.allclose(m["J_regressor"].sum(1), torch.ones(16), atol=1e-5)
+    assert a.sampler == dict(near=0.0, N_samples=16, N_samples_eval=32, N_samples_extra=8, eps=0.1, beta_iters=10,
+                             max_total_iters=5, add_tiny=1e-6)
+
+
+def test_mirror_state_dict_keys_match_reference_format():
+    from hold_b200 import synth
+    from hold_b200.model import ImplicitNet, LaplaceDensity, RenderingNet
+
+    for kind in ("hand", "object"):
+        net, rgb = ImplicitNet(kind), RenderingNet(kind)
+        keys = set(net.state_dict())
+        assert keys == {f"lin{l}.{p}" for l in range(9) for p in ("weight_g", "weight_v", "bias")}
+        net.load_state_dict(synth.make_sdf_state(kind, 0, 0.5), strict=True)
+        rgb.load_state_dict(synth.make_rgb_state(kind, 0), strict=True)
+        assert net.lin3.weight_v.shape == (217, 256) and net.lin8.weight_v.shape == (257, 256)
+        assert rgb.lin0.weight_v.shape[1] == (270 if kind == "hand" else 302)
+    assert list(LaplaceDensity().state_dict()) == ["beta"]
+
+
+def test_flop_accounting_matches_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.MAC_SDF_FULL == 524_544
+    assert abs(bench.flops_per_ray(5, ("right",)) / 1e6 - 916.0) < 1.0        # 916 MFLOP per hand-ray
+    assert abs(bench.flops_per_ray(5, ("right", "object")) / 1e9 - 1.834) < 0.002
+
+
+def test_shard_range_partitions_exactly():
+    from hold_b200.shard import shard_frames, shard_range
+
+    for n in (0, 1, 511, 512, 513, 4096, 262144, 262145):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert all(s % 512 == 0 for s, _ in spans if s < n)
+    assert sorted(sum((shard_frames(10, r, 3) for r in range(3)), [])) == list(range(10))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from hold_b200.shard import shard_range
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 4096 + 37
+    s, e = shard_range(n, rank, world)
+    mine = torch.zeros(n)
+    mine[s:e] = 1.0
+    dist.all_reduce(mine)                       # every ray owned by exactly one rank
+    t = torch.tensor([float(e - s)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)    # the bench's max-over-ranks reduction
+    q.put((rank, bool((mine == 1).all()), t.item()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(60) for p in ps]
+    assert all(ok for _, ok, _ in res) and all(p.exitcode == 0 for p in ps)
+    assert {r for r, _, _ in res} == {0, 1}

@@ -1,0 +1,76 @@
+"""CPU-only: the oracle (oracle/hold_oracle.py) against the committed golden fixtures, which were produced by the
+REFERENCE's own modules (oracle/ref_harness.py golden).  Same criteria as ref_harness.check()."""
+import glob
+import os
+
+import pytest
+import torch
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+def _close(a, b, tol=1e-4, tol_max=3e-3, w=None, frac_min=0.97):
+    a, b = a.float(), b.float()
+    d = (a - b).abs()
+    scale = max(1.0, b.abs().max().item())
+    frac = (d <= tol * scale).float().mean().item()
+    if w is not None:
+        m = w > 1e-4
+        while m.dim() < d.dim():
+            m = m.unsqueeze(-1)
+        d = d * m
+    return frac >= frac_min and d.max().item() <= tol_max * scale
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-3] for p in GOLD])
+def test_oracle_matches_reference_golden(path):
+    from hold_b200 import synth
+    from oracle import hold_oracle as O
+
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    rec = torch.load(path)
+    sc = synth.make_scene(**rec["scene_kwargs"])
+    for nid in sc.node_ids:
+        sc.beta[nid] = torch.tensor(rec["beta"])
+    ids = rec["ray_ids"][:48]  # a subset keeps the CPU suite short; the sampler flag is per call, so compare per-ray data loosely
+    outs, art = O.render_scene(sc, ray_ids=rec["ray_ids"])
+    for k, nid in enumerate(sc.node_ids):
+        assert torch.equal(art[nid]["tfs"], rec["art"][nid]["tfs"]) or _close(art[nid]["tfs"], rec["art"][nid]["tfs"], 1e-6, 1e-5)
+        assert _close(art[nid]["verts"], rec["art"][nid]["verts"], 1e-6, 1e-5)
+        n, g = outs[0]["nodes"][k], rec["nodes"][nid]
+        w = outs[0]["render"][k]["fg_weights"]
+        for key in ("z_vals", "sdf", "canonical_pts", "normal", "color"):
+            # per-sample tensors inherit the sampler's position noise (flat-PDF regions, tools/noise_floor.py)
+            assert _close(n[key], g[key], w=w, tol_max=1e-1, frac_min=0.9), f"{nid}.{key}"
+        for key in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
+            # (the golden file was written by the reference modules in another process: BLAS blocking differs by
+            #  batch shape, and at beta = 0.03 that alone moves ~5 % of the hand's pixels by up to 3e-3)
+            assert _close(outs[0]["render"][k][key], rec["render"][nid][key], tol_max=1e-2, frac_min=0.9), f"{nid}.render.{key}"
+    for key in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
+        d = (outs[0]["render"]["comp"][key] - rec["render"]["comp"][key]).abs()
+        assert d.mean().item() <= 3e-3 and d.max().item() <= 6e-2, f"comp.{key}"
+
+
+def test_oracle_edge_cases():
+    from oracle import hold_oracle as O
+
+    # ray that misses the bounding sphere -> error, not exit() (engine/ray_sampler.py:15-18)
+    with pytest.raises(O.RayMissesSphere):
+        O.sphere_far(torch.tensor([[10.0, 0.0, 0.0]]), torch.tensor([[0.0, 1.0, 0.0]]), 1.0)
+    # merge_factors drops (n-1) head / n tail samples (hold_utils.py:115-119)
+    R, S = 3, 5
+    fl = []
+    for k in range(3):
+        z = torch.sort(torch.rand(R, S), 1).values
+        fl.append(dict(color=torch.rand(R, S, 3), normal=torch.rand(R, S, 3), density=torch.rand(R, S, 1),
+                       semantics=torch.zeros(R, S, 4), z_vals=z))
+    m = O.merge_factors(fl)
+    assert m["z_vals"].shape == (R, 3 * S - 2 * 3 + 1) and (m["z_vals"][:, 1:] >= m["z_vals"][:, :-1]).all()
+    # Laplace density is 1/(2 beta) at the surface and monotone in -sdf
+    s = torch.linspace(-1, 1, 11)
+    d = O.laplace_density(s, torch.tensor(0.1))
+    assert abs(d[5].item() - 5.0) < 1e-6 and (d[:-1] >= d[1:]).all()
+    # knn contract: ascending squared distances, K smallest
+    p, v = torch.rand(7, 3), torch.rand(50, 3)
+    dd, ii = O.knn_points(p, v, 15)
+    assert (dd[:, 1:] >= dd[:, :-1]).all() and torch.allclose(dd, ((p[:, None] - v[ii]) ** 2).sum(-1))
