@@ -157,13 +157,19 @@ __device__ __forceinline__ uint32_t a_unit_off(int r, int j) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
 }
 
-__device__ __forceinline__ float softplus100_fast(float x, float& e_out) {
-  // kTcScaleA * Softplus(beta=100, threshold=20)(x): x if 100x > 20 else log1p(exp(100x))/100, MUFU ex2/lg2
-  float bx = x * 100.0f;
-  float e = __expf(fminf(bx, 20.0f));
-  e_out = e;
-  float sp = __logf(1.0f + e) * (0.01f * kTcScaleA);
-  return (bx > 20.0f) ? x * kTcScaleA : sp;
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// kTcScaleA * Softplus(beta=100)(z) in its overflow-free form max(z,0) + log1p(exp(-|100 z|))/100 (two MUFU ops).
+// nn.Softplus' threshold branch (returns z for 100 z > 20) differs from this by < 2.1e-11.
+// u_out = exp(-|100 z|) for the derivative.
+__device__ __forceinline__ float softplus100_fast(float z, float& u_out) {
+  const float t = z * (100.0f * 1.4426950408889634f);
+  const float u = mufu_ex2(-fabsf(t));
+  u_out = u;
+  const float L = mufu_lg2(1.0f + u);
+  return fmaf(L, 0.6931471805599453f * 0.01f * kTcScaleA, fmaxf(z, 0.f) * kTcScaleA);
 }
 
 // One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
@@ -188,44 +194,42 @@ __device__ __noinline__ float embed_val(int e, int comp, float px, float py, flo
 }
 
 constexpr int kTcW = 4;                        // epilogue warps per TMEM lane quarter
-constexpr int kTcCW = 64 / kTcW;               // accumulator columns per warp per 64-column chunk
+constexpr int kTcChunk = 32;                   // accumulator columns per epilogue->MMA hand-off (= one weight stage of k)
+constexpr int kTcCW = kTcChunk / kTcW;         // accumulator columns per warp per chunk
 constexpr int kTcEpiWarps = 4 * kTcW;
 constexpr int kTcEpiThreads = 32 * kTcEpiWarps;
 constexpr int kTcThreadsTotal = 64 + kTcEpiThreads;
 
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 
 template <int MODE>
 struct TcCfg {
-  static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;
+  static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;   // 64-wide SW128 A chunks in smem
+  static constexpr int kHandoffs = 2 * kAChunks;                 // 32-wide epilogue->MMA hand-offs
   static constexpr int kStages = (MODE == MLP_COLOR) ? 2 : 3;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
   static constexpr int kSmemW = kStages * kTcStageBytes;
-  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers + 1 KB alignment slack
+  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
-  constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages;
+  constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
   constexpr int RPP = (MODE == MLP_SDF_JVP) ? 4 : 1;
   constexpr int PPT = kTcRows / RPP;
-  constexpr int CW = kTcCW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
   const uint32_t sBar = sW + Cfg::kSmemW;
-  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NA;
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NHO;
   const uint32_t sTmemPtr = bDFull + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
-    for (int i = 0; i < NA; ++i) mbar_init(bAReady + 8 * i, kTcEpiThreads);
+    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, kTcEpiThreads);
     mbar_init(bDFull, 1);
     mbar_init(bDFull + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -273,12 +277,10 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * 256);
           const int nst = a.L[l].nst;
           for (int s = 0; s < nst; ++s) {
-            const int c = s >> 1;  // A chunk (64 k) of this 32-k stage
-            if ((s & 1) == 0) {
-              mbar_wait(bAReady + 8 * c, (a_par >> c) & 1, a.err, 2);
-              a_par ^= (1u << c);
-              tc_fence_after();
-            }
+            const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
+            mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2);  // hand-off s = columns [32 s, 32 s + 32)
+            a_par ^= (1u << s);
+            tc_fence_after();
             mbar_wait(bWFull + 8 * stage, phase, a.err, 3);
             tc_fence_after();
             const uint32_t wb = sW + stage * kTcStageBytes;
@@ -321,61 +323,57 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       // ---------------------------------------------------------- prologue: layer-0 A operand (this warp's columns)
       if (MODE != MLP_COLOR) {
         if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
-#pragma unroll
-        for (int jj = 0; jj < CW / 8; ++jj) {
+        for (int h = 0; h < 2; ++h) {
           float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(sub * CW + jj * 8 + i, comp, px, py, pz, a.embed_w);
+          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(h * 32 + sub * 8 + i, comp, px, py, pz, a.embed_w);
           uint4 hi, lo;
           split8(x, hi, lo);
-          const int j = sub * (CW / 8) + jj;
+          const int j = h * 4 + sub;
           *reinterpret_cast<uint4*>(gA_hi + a_unit_off(row, j)) = hi;
           *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, j)) = lo;
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bAReady);
-      } else {
-        const int b = valid ? p / a.pts_per_frame : 0;
-        for (int c = 0; c < 5; ++c) {
-#pragma unroll
-          for (int jj = 0; jj < CW / 8; ++jj) {
-            float x[8];
-            const int k0 = c * 64 + sub * CW + jj * 8;
-            if (c < 4) {
-              if (valid) {
-                const float4 f0 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0);
-                const float4 f1 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0 + 4);
-                x[0] = f0.x, x[1] = f0.y, x[2] = f0.z, x[3] = f0.w, x[4] = f1.x, x[5] = f1.y, x[6] = f1.z, x[7] = f1.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
-                float v = 0.f;
-                if (valid) {
-                  if (e < 3) v = a.xc[3 * (size_t)p + e];
-                  else if (e < 6) v = a.normal[3 * (size_t)p + e - 3];
-                  else if (e < 14) v = (a.pose_embed != nullptr) ? a.pose_embed[b * 8 + e - 6] : 0.f;
-                  else if (e < a.k0 - kFeat) v = a.time_code[b * 32 + e - 14];
-                }
-                x[i] = v;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] *= kTcScaleA;
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int j = sub * (CW / 8) + jj;
-            *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
-            *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-          }
           fence_proxy_async();
           tc_fence_before();
-          mbar_arrive(bAReady + 8 * c);
+          mbar_arrive(bAReady + 8 * h);
+        }
+      } else {
+        const int b = valid ? p / a.pts_per_frame : 0;
+        for (int h = 0; h < 10; ++h) {
+          float x[8];
+          const int k0 = h * 32 + sub * 8;
+          if (h < 8) {
+            if (valid) {
+              const float4 f0 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0);
+              const float4 f1 = *reinterpret_cast<const float4*>(a.feat + (size_t)p * kFeat + k0 + 4);
+              x[0] = f0.x, x[1] = f0.y, x[2] = f0.z, x[3] = f0.w, x[4] = f1.x, x[5] = f1.y, x[6] = f1.z, x[7] = f1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
+              float v = 0.f;
+              if (valid) {
+                if (e < 3) v = a.xc[3 * (size_t)p + e];
+                else if (e < 6) v = a.normal[3 * (size_t)p + e - 3];
+                else if (e < 14) v = (a.pose_embed != nullptr) ? a.pose_embed[b * 8 + e - 6] : 0.f;
+                else if (e < a.k0 - kFeat) v = a.time_code[b * 32 + e - 14];
+              }
+              x[i] = v;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] *= kTcScaleA;
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int c = h >> 1, j = (h & 1) * 4 + sub;
+          *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+          *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bAReady + 8 * h);
         }
       }
       // ---------------------------------------------------------- per-layer epilogues
@@ -389,23 +387,25 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         d_par ^= (1u << (l & 1));
         tc_fence_after();
         const float* bias = a.L[l].bias;
-        for (int c = 0; c < 4; ++c) {
-          const int n0 = c * 64 + sub * CW;
-          uint32_t raw[CW];
-          tc_ld16(t_lane + (uint32_t)((l & 1) * 256 + n0), raw);
-          float bv[CW];
-#pragma unroll
-          for (int i = 0; i < CW / 4; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-            bv[4 * i] = b4.x, bv[4 * i + 1] = b4.y, bv[4 * i + 2] = b4.z, bv[4 * i + 3] = b4.w;
-          }
+        const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
+        uint32_t raw[8];
+        tc_ld8(t_col, raw);
+        for (int h = 0; h < 8; ++h) {
+          const int n0 = h * 32 + sub * 8;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           tc_wait_ld();
-          float out[CW];
+          float acc[8];
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
+          for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]);
+          if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);  // prefetch the next hand-off's columns
+          float out[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
             // accumulator -> pre-activation (undo the operand scaling, add the bias on value rows); out[] holds the
             // next layer's operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
-            const float z = fmaf(__uint_as_float(raw[i]), kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
+            const float z = fmaf(acc[i], kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
             float o;
             if (MODE == MLP_COLOR) {
               o = fmaxf(z, 0.f) * kTcScaleA;
@@ -415,8 +415,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               float e;
               const float sp = softplus100_fast(z, e);
               if (MODE == MLP_SDF_JVP) {
-                // softplus'(z) = e/(1+e) of the VALUE row (lane & ~3), applied to the tangent rows
-                const float s = (z * 100.0f > 20.0f) ? kTcScaleA : __fdividef(e * kTcScaleA, 1.0f + e);
+                // softplus'(z) of the VALUE row (lane & ~3), applied to the tangent rows
+                const float r = mufu_rcp(1.0f + e) * kTcScaleA;   // e = exp(-|100 z|)
+                const float s = (z >= 0.f) ? r : e * r;            // = kTcScaleA * sigmoid(100 z)
                 const float sv = __shfl_sync(0xffffffffu, s, lane & ~3);
                 o = is_value ? sp : z * sv;
               } else {
@@ -425,14 +426,14 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             }
             out[i] = o;
           }
-          if (MODE != MLP_COLOR && n0 + CW > N) {  // skip connection: embedding columns of layer 3's output
+          if (MODE != MLP_COLOR && n0 + 8 > N) {  // skip connection: embedding columns of layer 3's output
 #pragma unroll
-            for (int i = 0; i < CW; ++i)
+            for (int i = 0; i < 8; ++i)
               if (n0 + i >= N) out[i] = kTcScaleA * embed_val(n0 + i - N, comp, px, py, pz, a.embed_w);
           }
           if (head_layer) {
 #pragma unroll
-            for (int i = 0; i < CW / 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
               head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
               if (MODE == MLP_COLOR) {
@@ -446,21 +447,18 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           if (feat_layer) {
             if (valid && is_value) {
               float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
-#pragma unroll
-              for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+              dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+              dst[1] = make_float4(out[4], out[5], out[6], out[7]);
             }
           } else if (!last_mma) {
-#pragma unroll
-            for (int jj = 0; jj < CW / 8; ++jj) {
-              uint4 hi, lo;
-              split8(out + 8 * jj, hi, lo);
-              const int j = sub * (CW / 8) + jj;
-              *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
-              *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-            }
+            uint4 hi, lo;
+            split8(out, hi, lo);
+            const int c = h >> 1, j = (h & 1) * 4 + sub;
+            *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+            *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bAReady + 8 * c);
+            mbar_arrive(bAReady + 8 * h);
           }
         }
       }
