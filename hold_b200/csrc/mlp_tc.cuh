@@ -1,6 +1,10 @@
 // tcgen05 (5th-gen tensor core) fused MLP chains — HOLD_MLP_TC.
 //
-// One persistent CTA per SM walks 128-row tiles through the whole layer chain:
+// Persistent CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2): each CTA of a pair walks its own 128-row tile through
+// the whole layer chain while the pair shares every weight stage — an M=256 MMA reads rows [0,128) of B from the
+// leader's shared memory and rows [128,256) from the peer's, which halves both the L2->smem weight traffic and the
+// shared-memory read bandwidth of the three MMA passes (the single-CTA version was smem-bandwidth bound at 60 %).
+// Per CTA:
 //   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled fp16 weight chunks L2 -> smem ring
 //   * warp 1 (1 lane)  : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
 //   * warps 2..5       : epilogue — tcgen05.ld the accumulator in 64-column chunks, bias + activation in fp32,
@@ -22,7 +26,8 @@
 namespace hold {
 
 constexpr int kTcRows = 128;
-constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] bf16 hi (16 KB) + lo (16 KB)
+constexpr int kTcStageBytes = 32768;      // one weight stage in HBM: [256 n x 32 k] fp16, per CTA half: hi (8 KB) + lo (8 KB)
+constexpr int kTcHalfStage = 16384;       // what one CTA of the pair stages: rows [128 r, 128 r + 128) of B
 constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] bf16
 constexpr int kTcThreads = 192;
 // Power-of-two operand scaling (exact): fp16 operands are fed to the tensor core as A * 2^6 and W * 2^10 so that
@@ -74,21 +79,39 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  // shared::cta address -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.  On a timeout the waiter
+// records its tag in the device error word and raises the CTA pair's abort flags (shared memory); every other wait
+// polls that flag, so the kernel drains in microseconds and hold_ctx_check() reports HOLD_E_STATE.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag, volatile int* abort_flag) {
   uint32_t done = 0;
   for (unsigned spin = 0; spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (done) return;
+    if (done) return true;
+    if ((spin & 63) == 63 && *abort_flag) return false;
   }
   if (err != nullptr) atomicOr(err, 0x100 | (tag << 12));
-  __trap();
+  *abort_flag = 1;
+  const uint32_t peer = mapa_rank(smem_u32((const void*)abort_flag), cluster_ctarank() ^ 1u);
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer), "r"(1u) : "memory");
+  return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -98,14 +121,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// completion of all previously issued MMAs -> one arrival on the barrier at the same smem offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -135,8 +161,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
-// kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=128
-constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=256 (cta_group::2)
+constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the CTA pair
 
 // x = hi + lo: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
@@ -212,14 +238,14 @@ template <int MODE>
 struct TcCfg {
   static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;   // 64-wide SW128 A chunks in smem
   static constexpr int kHandoffs = 2 * kAChunks;                 // 32-wide epilogue->MMA hand-offs
-  static constexpr int kStages = (MODE == MLP_COLOR) ? 2 : 3;
+  static constexpr int kStages = (MODE == MLP_COLOR) ? 4 : 6;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
-  static constexpr int kSmemW = kStages * kTcStageBytes;
-  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
+  static constexpr int kSmemW = kStages * kTcHalfStage;
+  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*6 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
@@ -229,39 +255,46 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
   const uint32_t sBar = sW + Cfg::kSmemW;
-  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NHO;
-  const uint32_t sTmemPtr = bDFull + 16;
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bWPeer = sBar + 16 * NS, bAReady = sBar + 24 * NS, bDFull = bAReady + 8 * NHO;
+  const uint32_t sTmemPtr = bDFull + 16, sAbort = bDFull + 20;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = ceil_div(a.P, PPT);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(gen_base + (sAbort - base));
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int n_pairs = ceil_div(ceil_div(a.P, PPT), 2);
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
-    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, kTcEpiThreads);
+    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); mbar_init(bWPeer + 8 * i, 1); }
+    *abort_flag = 0;
+    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, 2 * kTcEpiThreads);  // both CTAs' epilogue threads
     mbar_init(bDFull, 1);
     mbar_init(bDFull + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  cluster_sync_all();
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
 
   if (warp == 0) {
     // ============================================================ weight producer (TMA engine, bulk async copies)
     if (lane == 0) {
+      // Each CTA stages ITS half of B on its own full barrier; the peer's warp 1 forwards "my half has landed" to
+      // the leader (bWPeer); the stage is released in both CTAs by the multicast commit.
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
         for (int l = 0; l < a.n_layers; ++l) {
-          const uint8_t* src = a.L[l].wimg;
+          const uint8_t* src = a.L[l].wimg + (size_t)rank * kTcHalfStage;
           for (int s = 0; s < a.L[l].nst; ++s) {
-            mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1);
-            mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
-            bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
+            if (!mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag)) goto tc_done;
+            mbar_expect_tx(bWFull + 8 * stage, kTcHalfStage);
+            bulk_g2s(sW + stage * kTcHalfStage, src + (size_t)s * kTcStageBytes, kTcHalfStage, bWFull + 8 * stage);
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
@@ -269,28 +302,40 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank == 1) {
+      // peer CTA: forward the arrival of its weight halves to the leader's MMA issuer
+      uint32_t stage = 0, phase = 0;
+      const uint32_t peer_bar = mapa_rank(bWPeer, 0);
+      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters)
+        for (int l = 0; l < a.n_layers; ++l)
+          for (int s = 0; s < a.L[l].nst; ++s) {
+            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 5, abort_flag)) goto tc_done;
+            mbar_arrive_cluster(peer_bar + 8 * stage);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+    }
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_par = 0;  // bit c = parity to wait for on a_ready[c]
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
         for (int l = 0; l < a.n_layers; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * 256);
           const int nst = a.L[l].nst;
           for (int s = 0; s < nst; ++s) {
             const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
-            mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2);  // hand-off s = columns [32 s, 32 s + 32)
+            if (!mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag)) goto tc_done;  // hand-off s = columns [32 s, 32 s + 32)
             a_par ^= (1u << s);
+            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag)) goto tc_done;
+            if (!mbar_wait(bWPeer + 8 * stage, phase, a.err, 6, abort_flag)) goto tc_done;
             tc_fence_after();
-            mbar_wait(bWFull + 8 * stage, phase, a.err, 3);
-            tc_fence_after();
-            const uint32_t wb = sW + stage * kTcStageBytes;
+            const uint32_t wb = sW + stage * kTcHalfStage;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
               const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
               const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
               const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
-              const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
+              const uint64_t wlo = umma_desc(wb + 8192 + j * 32, 512, kLayoutSW64);
               tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
               tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
               tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
@@ -316,7 +361,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
     const int comp = row % RPP;
     const bool is_value = (comp == 0);
     uint32_t d_par = 0;  // bit b = parity to wait for on d_full[b]
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t bAReadyLeader = mapa_rank(bAReady, 0);  // hand-off barriers live in the leader CTA
+    for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
+      const int tile = 2 * tp + (int)rank;
       const int p = tile * PPT + row / RPP;
       const bool valid = p < a.P;
       float px = 0.f, py = 0.f, pz = 0.f;
@@ -334,7 +381,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, j)) = lo;
           fence_proxy_async();
           tc_fence_before();
-          mbar_arrive(bAReady + 8 * h);
+          mbar_arrive_cluster(bAReadyLeader + 8 * h);
         }
       } else {
         const int b = valid ? p / a.pts_per_frame : 0;
@@ -373,7 +420,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
           fence_proxy_async();
           tc_fence_before();
-          mbar_arrive(bAReady + 8 * h);
+          mbar_arrive_cluster(bAReadyLeader + 8 * h);
         }
       }
       // ---------------------------------------------------------- per-layer epilogues
@@ -383,7 +430,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         const bool head_layer = (MODE == MLP_COLOR) ? (l == a.n_layers - 1) : (l == 7);
         const bool last_mma = (l == a.n_layers - 1);
         const int N = a.L[l].N;
-        mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4);
+        if (!mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag)) break;
         d_par ^= (1u << (l & 1));
         tc_fence_after();
         const float* bias = a.L[l].bias;
@@ -458,7 +505,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bAReady + 8 * h);
+            mbar_arrive_cluster(bAReadyLeader + 8 * h);
           }
         }
       }
@@ -492,11 +539,12 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       epi_bar();  // scratch is overwritten by the next tile's prologue
     }
   }
+tc_done:
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // the peer's TMEM/smem must outlive the leader's last MMA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -538,11 +586,17 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
     __half h = __float2half_rn(w);
     __half l = __float2half_rn(w - __half2float(h));
     const int st = k >> 5, kk = k & 31;
-    const size_t off = (size_t)st * kTcStageBytes + (size_t)((n >> 3) * 512 + (n & 7) * 64 + ((((kk >> 3) ^ ((n >> 1) & 3))) << 4) + (kk & 7) * 2);
+    // stage = [CTA0 half: hi 8 KB | lo 8 KB][CTA1 half: hi | lo]; a half holds rows n in [128 r, 128 r + 128)
+    const int r = n >> 7, nl = n & 127;
+    const size_t off = (size_t)st * kTcStageBytes + (size_t)r * kTcHalfStage +
+                       (size_t)((nl >> 3) * 512 + (nl & 7) * 64 + ((((kk >> 3) ^ ((nl >> 1) & 3))) << 4) + (kk & 7) * 2);
     *reinterpret_cast<__half*>(img + off) = h;
-    *reinterpret_cast<__half*>(img + off + 16384) = l;
+    *reinterpret_cast<__half*>(img + off + 8192) = l;
   }
 }
+
+// grid of CTA pairs: even, at most one CTA per SM
+static inline int tc_grid(int tiles, int sm_count) { return 2 * max(1, min(ceil_div(tiles, 2), sm_count / 2)); }
 
 static int tc_init(hold_ctx*) {
   cudaError_t e;
@@ -600,10 +654,10 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   if (jvp) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     int tiles = ceil_div(P, kTcRows / 4);
-    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_JVP><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
   } else {
     int tiles = ceil_div(P, kTcRows);
-    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_ONLY><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
@@ -621,7 +675,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
   a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err;
   int tiles = ceil_div(P, kTcRows);
-  k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
+  k_mlp_tc<MLP_COLOR><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }
