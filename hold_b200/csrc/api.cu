@@ -1,6 +1,7 @@
 // C ABI of hold_b200 (include/hold_b200.h): context, weight packing, launch sequences.  Host-side logic
 // only — every arithmetic step of the path lives in the kernels included below.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <new>
 
 #include "common.cuh"
@@ -20,9 +21,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-enum WsSlot { WS_Z = 0, WS_SDF, WS_ZNEW, WS_SDFNEW, WS_BETA, WS_FAR, WS_XC, WS_SSDF, WS_GRAD, WS_FEAT, WS_PE, WS_ZTMP, WS_COUNT };
+enum WsSlot { WS_Z = 0, WS_SDF, WS_ZNEW, WS_SDFNEW, WS_BETA, WS_FAR, WS_XC, WS_SSDF, WS_GRAD, WS_FEAT, WS_PE, WS_ZTMP, WS_SIG, WS_COUNT };
 
-static int ws_get(hold_ctx* ctx, int slot, size_t bytes, void** out) {
+int ws_get(hold_ctx* ctx, int slot, size_t bytes, void** out) {
   Buffer& b = ctx->ws[slot];
   if (b.bytes < bytes) {
     if (b.p) HOLD_CUDA(cudaFree(b.p));

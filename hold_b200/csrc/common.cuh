@@ -74,6 +74,7 @@ struct hold_ctx {
 namespace hold {
 
 void set_error(const char* fmt, ...);
+int ws_get(hold_ctx* ctx, int slot, size_t bytes, void** out);  // grow-only workspace (api.cu)
 #define HOLD_CUDA(expr)                                                                   \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

@@ -11,7 +11,7 @@
 
 namespace hold {
 
-enum { MLP_SDF_ONLY = 0, MLP_SDF_JVP = 1, MLP_COLOR = 2 };
+enum { MLP_SDF_ONLY = 0, MLP_SDF_JVP = 1, MLP_COLOR = 2, MLP_SDF_REV = 3 };
 
 constexpr int kTileRows = 64;
 constexpr int kActLd = 308;   // >= 304 (colour-net input 302 -> 304) + 4

@@ -1,10 +1,6 @@
 // tcgen05 (5th-gen tensor core) fused MLP chains — HOLD_MLP_TC.
 //
-// Persistent CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2): each CTA of a pair walks its own 128-row tile through
-// the whole layer chain while the pair shares every weight stage — an M=256 MMA reads rows [0,128) of B from the
-// leader's shared memory and rows [128,256) from the peer's, which halves both the L2->smem weight traffic and the
-// shared-memory read bandwidth of the three MMA passes (the single-CTA version was smem-bandwidth bound at 60 %).
-// Per CTA:
+// One persistent CTA per SM walks 128-row tiles through the whole layer chain:
 //   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled fp16 weight chunks L2 -> smem ring
 //   * warp 1 (1 lane)  : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
 //   * warps 2..5       : epilogue — tcgen05.ld the accumulator in 64-column chunks, bias + activation in fp32,
@@ -26,8 +22,7 @@
 namespace hold {
 
 constexpr int kTcRows = 128;
-constexpr int kTcStageBytes = 32768;      // one weight stage in HBM: [256 n x 32 k] fp16, per CTA half: hi (8 KB) + lo (8 KB)
-constexpr int kTcHalfStage = 16384;       // what one CTA of the pair stages: rows [128 r, 128 r + 128) of B
+constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] bf16 hi (16 KB) + lo (16 KB)
 constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] bf16
 constexpr int kTcThreads = 192;
 // Power-of-two operand scaling (exact): fp16 operands are fed to the tensor core as A * 2^6 and W * 2^10 so that
@@ -36,6 +31,7 @@ constexpr int kTcThreads = 192;
 // rescaled by 2^-16 in the epilogue's bias FMA.  Range: |a| < 1023, |w| < 64.
 constexpr float kTcScaleA = 64.0f, kTcScaleW = 1024.0f, kTcUnscale = 1.0f / (64.0f * 1024.0f);
 
+constexpr int kTcMaxSteps = 17;
 struct TcLayer {
   const uint8_t* wimg;  // pre-swizzled stage images, nst * 32 KB
   const float* bias;    // [256]
@@ -46,12 +42,14 @@ struct TcLayer {
 struct TcMlp {
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
+  uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient
   int sdf_nst[HOLD_MAX_LAYERS], rgb_nst[HOLD_MAX_LAYERS];
 };
 
 struct TcArgs {
   int P, n_layers;
-  TcLayer L[HOLD_MAX_LAYERS];
+  TcLayer L[kTcMaxSteps];
+  float* sig;  // reverse mode: per-CTA stash of softplus'(z_l), [grid][8][128][256] fp32
   const float* w_last;
   const float* b_last;
   const float* xc;
@@ -79,27 +77,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  // shared::cta address -> shared::cluster address in CTA `rank`
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.  On a timeout the waiter
-// records its tag in the device error word and raises the CTA pair's abort flags (shared memory); every other wait
-// polls that flag, so the kernel drains in microseconds and hold_ctx_check() reports HOLD_E_STATE.
+// records its tag in the device error word and raises the CTA's abort flag (shared memory); every other wait polls
+// that flag, so the kernel drains in microseconds and hold_ctx_check() reports HOLD_E_STATE.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag, volatile int* abort_flag) {
   uint32_t done = 0;
   for (unsigned spin = 0; spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -109,8 +95,6 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
   if (err != nullptr) atomicOr(err, 0x100 | (tag << 12));
   *abort_flag = 1;
-  const uint32_t peer = mapa_rank(smem_u32((const void*)abort_flag), cluster_ctarank() ^ 1u);
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer), "r"(1u) : "memory");
   return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -121,17 +105,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// completion of all previously issued MMAs -> one arrival on the barrier at the same smem offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -161,8 +142,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
-// kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=256 (cta_group::2)
-constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);  // M = 256 over the CTA pair
+// kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=128
+constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 // x = hi + lo: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
@@ -232,17 +213,13 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
-// One arrival per epilogue WARP on the leader's hand-off barrier: every lane orders its own st.shared against the
-// async proxy, the warp converges, lane 0 arrives (locally in the leader, through DSMEM from the peer).  1024
-// cluster-scope arrivals per hand-off made the 2-CTA version 40 % slower than the single-CTA one.
-__device__ __forceinline__ void handoff_arrive(uint32_t local_bar, uint32_t leader_bar, uint32_t rank, int lane) {
+// One arrival per epilogue WARP on the hand-off barrier: every lane orders its own st.shared against the async
+// proxy, the warp converges, lane 0 arrives.
+__device__ __forceinline__ void handoff_arrive(uint32_t bar, int lane) {
   fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) {
-    if (rank == 0) mbar_arrive(local_bar);
-    else mbar_arrive_cluster(leader_bar);
-  }
+  if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 
@@ -250,14 +227,14 @@ template <int MODE>
 struct TcCfg {
   static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;   // 64-wide SW128 A chunks in smem
   static constexpr int kHandoffs = 2 * kAChunks;                 // 32-wide epilogue->MMA hand-offs
-  static constexpr int kStages = (MODE == MLP_COLOR) ? 4 : 6;
+  static constexpr int kStages = (MODE == MLP_COLOR) ? 2 : 3;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
-  static constexpr int kSmemW = kStages * kTcHalfStage;
-  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*6 + 10 + 2, 8 B each) + 1 KB alignment slack
+  static constexpr int kSmemW = kStages * kTcStageBytes;
+  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
+__global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
@@ -267,46 +244,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
   const uint32_t sBar = sW + Cfg::kSmemW;
-  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bWPeer = sBar + 16 * NS, bAReady = sBar + 24 * NS, bDFull = bAReady + 8 * NHO;
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NHO;
   const uint32_t sTmemPtr = bDFull + 16, sAbort = bDFull + 20;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   volatile int* abort_flag = reinterpret_cast<volatile int*>(gen_base + (sAbort - base));
-  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
-  const int n_pairs = ceil_div(ceil_div(a.P, PPT), 2);
-  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int n_tiles = ceil_div(a.P, PPT);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); mbar_init(bWPeer + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
     *abort_flag = 0;
-    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, 2 * kTcEpiWarps);  // one arrival per epilogue warp of both CTAs
+    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, kTcEpiWarps);  // one arrival per epilogue warp
     mbar_init(bDFull, 1);
     mbar_init(bDFull + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  cluster_sync_all();
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  cluster_sync_all();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
 
   if (warp == 0) {
     // ============================================================ weight producer (TMA engine, bulk async copies)
     if (lane == 0) {
-      // Each CTA stages ITS half of B on its own full barrier; the peer's warp 1 forwards "my half has landed" to
-      // the leader (bWPeer); the stage is released in both CTAs by the multicast commit.
       uint32_t stage = 0, phase = 0;
-      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < a.n_layers; ++l) {
-          const uint8_t* src = a.L[l].wimg + (size_t)rank * kTcHalfStage;
+          const uint8_t* src = a.L[l].wimg;
           for (int s = 0; s < a.L[l].nst; ++s) {
             if (!mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag)) goto tc_done;
-            mbar_expect_tx(bWFull + 8 * stage, kTcHalfStage);
-            bulk_g2s(sW + stage * kTcHalfStage, src + (size_t)s * kTcStageBytes, kTcHalfStage, bWFull + 8 * stage);
+            mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
+            bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
@@ -314,22 +286,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (lane == 0 && rank == 1) {
-      // peer CTA: forward the arrival of its weight halves to the leader's MMA issuer
-      uint32_t stage = 0, phase = 0;
-      const uint32_t peer_bar = mapa_rank(bWPeer, 0);
-      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters)
-        for (int l = 0; l < a.n_layers; ++l)
-          for (int s = 0; s < a.L[l].nst; ++s) {
-            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 5, abort_flag)) goto tc_done;
-            mbar_arrive_cluster(peer_bar + 8 * stage);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-          }
-    }
-    if (lane == 0 && rank == 0) {
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t a_par = 0;  // bit c = parity to wait for on a_ready[c]
-      for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < a.n_layers; ++l) {
           const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * 256);
           const int nst = a.L[l].nst;
@@ -337,17 +297,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
             const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
             if (!mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag)) goto tc_done;  // hand-off s = columns [32 s, 32 s + 32)
             a_par ^= (1u << s);
-            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag)) goto tc_done;
-            if (!mbar_wait(bWPeer + 8 * stage, phase, a.err, 6, abort_flag)) goto tc_done;
             tc_fence_after();
-            const uint32_t wb = sW + stage * kTcHalfStage;
+            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag)) goto tc_done;
+            tc_fence_after();
+            const uint32_t wb = sW + stage * kTcStageBytes;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
               const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
               const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
               const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
-              const uint64_t wlo = umma_desc(wb + 8192 + j * 32, 512, kLayoutSW64);
+              const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
               tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
               tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
               tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
@@ -373,9 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     const int comp = row % RPP;
     const bool is_value = (comp == 0);
     uint32_t d_par = 0;  // bit b = parity to wait for on d_full[b]
-    const uint32_t bAReadyLeader = mapa_rank(bAReady, 0);  // hand-off barriers live in the leader CTA
-    for (int tp = cluster_id; tp < n_pairs; tp += n_clusters) {
-      const int tile = 2 * tp + (int)rank;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int p = tile * PPT + row / RPP;
       const bool valid = p < a.P;
       float px = 0.f, py = 0.f, pz = 0.f;
@@ -391,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
           const int j = h * 4 + sub;
           *reinterpret_cast<uint4*>(gA_hi + a_unit_off(row, j)) = hi;
           *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, j)) = lo;
-          handoff_arrive(bAReady + 8 * h, bAReadyLeader + 8 * h, rank, lane);
+          handoff_arrive(bAReady + 8 * h, lane);
         }
       } else {
         const int b = valid ? p / a.pts_per_frame : 0;
@@ -428,11 +386,143 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
           const int c = h >> 1, j = (h & 1) * 4 + sub;
           *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
           *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-          handoff_arrive(bAReady + 8 * h, bAReadyLeader + 8 * h, rank, lane);
+          handoff_arrive(bAReady + 8 * h, lane);
         }
       }
       // ---------------------------------------------------------- per-layer epilogues
-      float head0 = 0.f, head1 = 0.f, head2 = 0.f;
+      float head0 = 0.f, head1 = 0.f, head2 = 0.f, gz_acc = 0.f;
+      if (MODE == MLP_SDF_REV) {
+        // ======== reverse-mode gradient: 8 forward layers (stash softplus'), feature layer, 8 backward layers ========
+        // d sdf/d z_7 = w_sdf * s_7;  d sdf/d z_{l-1} = (g_l . W_l) * s_{l-1};  embedding columns (skip input of
+        // layer 4, input of layer 0) collect d sdf/d embed, chained with d embed/d x_c per column.
+        float* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
+        for (int st = 0; st < 17; ++st) {
+          if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) break;
+          d_par ^= (1u << (st & 1));
+          tc_fence_after();
+          const int kind = (st < 8) ? 0 : ((st == 8) ? 1 : ((st < 16) ? 2 : 3));
+          const int l = (st <= 8) ? st : 16 - st;
+          const float* bias = a.L[st].bias;
+          const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 8);
+          uint32_t raw[8];
+          tc_ld8(t_col, raw);
+          for (int h = 0; h < 8; ++h) {
+            const int n0 = h * 32 + sub * 8;
+            float bv[8];
+            if (kind <= 1) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+              bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w, bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
+            } else if (kind == 2) {  // softplus'(z_{l-1}) of this row
+              const float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)(l - 1) * (kTcRows * 256) + n0);
+              const float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)(l - 1) * (kTcRows * 256) + n0 + 4);
+              bv[0] = s0.x, bv[1] = s0.y, bv[2] = s0.z, bv[3] = s0.w, bv[4] = s1.x, bv[5] = s1.y, bv[6] = s1.z, bv[7] = s1.w;
+            }
+            tc_wait_ld();
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * kTcUnscale;
+            if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
+            float out[8];
+            if (kind == 0) {
+              float sg[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float z = acc[i] + bv[i];
+                float e;
+                out[i] = softplus100_fast(z, e);
+                const float r = mufu_rcp(1.0f + e);
+                sg[i] = (z >= 0.f) ? r : e * r;
+              }
+              *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+              *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0 + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+              if (l == 3 && n0 + 8 > 217) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (n0 + i >= 217) out[i] = kTcScaleA * embed_val(n0 + i - 217, 0, px, py, pz, a.embed_w);
+              }
+              if (l == 7) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
+                  head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
+                }
+              }
+            } else if (kind == 1) {
+              if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
+                dst[0] = make_float4(acc[0] + bv[0], acc[1] + bv[1], acc[2] + bv[2], acc[3] + bv[3]);
+                dst[1] = make_float4(acc[4] + bv[4], acc[5] + bv[5], acc[6] + bv[6], acc[7] + bv[7]);
+              }
+              const float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0);
+              const float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0 + 4);
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
+              out[0] = kTcScaleA * w0.x * s0.x, out[1] = kTcScaleA * w0.y * s0.y, out[2] = kTcScaleA * w0.z * s0.z, out[3] = kTcScaleA * w0.w * s0.w;
+              out[4] = kTcScaleA * w1.x * s1.x, out[5] = kTcScaleA * w1.y * s1.y, out[6] = kTcScaleA * w1.z * s1.z, out[7] = kTcScaleA * w1.w * s1.w;
+            } else if (kind == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) out[i] = kTcScaleA * acc[i] * bv[i];
+              if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (n0 + i >= 217) {
+                    const int e = n0 + i - 217, d = e % 3;
+                    const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
+                    head1 += (d == 0) ? je : 0.f;
+                    head2 += (d == 1) ? je : 0.f;
+                    gz_acc += (d == 2) ? je : 0.f;
+                    out[i] = 0.f;
+                  }
+                }
+              }
+            } else {  // kind 3: d sdf / d embed through layer 0's input
+              if (n0 < 40) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int e = n0 + i;
+                  if (e < kEmbed) {
+                    const int d = e % 3;
+                    const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
+                    head1 += (d == 0) ? je : 0.f;
+                    head2 += (d == 1) ? je : 0.f;
+                    gz_acc += (d == 2) ? je : 0.f;
+                  }
+                }
+              }
+            }
+            if (st < 16) {
+              uint4 hi, lo;
+              split8(out, hi, lo);
+              const int c = h >> 1, j = (h & 1) * 4 + sub;
+              *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+              *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+              handoff_arrive(bAReady + 8 * h, lane);
+            }
+          }
+        }
+        // fixed-order reduction of (sdf head, d/dx, d/dy, d/dz) over the quarter's 4 warps
+        tc_fence_before();
+        scratch[(sub * 4 + 0) * kTcRows + row] = head0;
+        scratch[(sub * 4 + 1) * kTcRows + row] = head1;
+        scratch[(sub * 4 + 2) * kTcRows + row] = head2;
+        scratch[(sub * 4 + 3) * kTcRows + row] = gz_acc;
+        epi_bar();
+        if (sub == 0 && valid) {
+          float hsum[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTcW; ++w) acc += scratch[(w * 4 + k) * kTcRows + row];
+            hsum[k] = acc;
+          }
+          a.sdf[p] = hsum[0] * (1.0f / kTcScaleA) + a.b_last[0];
+          a.grad[3 * (size_t)p] = hsum[1], a.grad[3 * (size_t)p + 1] = hsum[2], a.grad[3 * (size_t)p + 2] = hsum[3];
+        }
+        epi_bar();
+        continue;
+      }
       for (int l = 0; l < a.n_layers; ++l) {
         const bool feat_layer = (MODE == MLP_SDF_JVP) && (l == a.n_layers - 1);
         const bool head_layer = (MODE == MLP_COLOR) ? (l == a.n_layers - 1) : (l == 7);
@@ -511,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
             const int c = h >> 1, j = (h & 1) * 4 + sub;
             *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
             *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-            handoff_arrive(bAReady + 8 * h, bAReadyLeader + 8 * h, rank, lane);
+            handoff_arrive(bAReady + 8 * h, lane);
           }
         }
       }
@@ -547,10 +637,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
   }
 tc_done:
   tc_fence_before();
-  cluster_sync_all();  // the peer's TMEM/smem must outlive the leader's last MMA
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -592,23 +682,43 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
     __half h = __float2half_rn(w);
     __half l = __float2half_rn(w - __half2float(h));
     const int st = k >> 5, kk = k & 31;
-    // stage = [CTA0 half: hi 8 KB | lo 8 KB][CTA1 half: hi | lo]; a half holds rows n in [128 r, 128 r + 128)
-    const int r = n >> 7, nl = n & 127;
-    const size_t off = (size_t)st * kTcStageBytes + (size_t)r * kTcHalfStage +
-                       (size_t)((nl >> 3) * 512 + (nl & 7) * 64 + ((((kk >> 3) ^ ((nl >> 1) & 3))) << 4) + (kk & 7) * 2);
+    const size_t off = (size_t)st * kTcStageBytes + (size_t)((n >> 3) * 512 + (n & 7) * 64 + ((((kk >> 3) ^ ((n >> 1) & 3))) << 4) + (kk & 7) * 2);
     *reinterpret_cast<__half*>(img + off) = h;
-    *reinterpret_cast<__half*>(img + off + 8192) = l;
+    *reinterpret_cast<__half*>(img + off + 16384) = l;
   }
 }
 
-// grid of CTA pairs: even, at most one CTA per SM
-static inline int tc_grid(int tiles, int sm_count) { return 2 * max(1, min(ceil_div(tiles, 2), sm_count / 2)); }
+// Transposed image for the reverse-mode gradient: B rows = input index k_in of layer l, K = output index n_out:
+// WT[k_in][n_out] = kTcScaleW * scale * fold(v, g)[n_out][k_in]  (zero outside [N_out) x [K_in)).
+__global__ void k_tc_pack_T(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int N_out, int K_in,
+                            float scale, uint8_t* __restrict__ img) {
+  const int r = blockIdx.x;   // k_in, 0..255
+  const int n = threadIdx.x;  // n_out, 0..255
+  float w = 0.f;
+  if (n < N_out && r < K_in) {
+    const float* vr = v + (size_t)n * in_dim;
+    float f = 1.0f;
+    if (g != nullptr) {
+      float ss = 0.f;
+      for (int k = 0; k < in_dim; ++k) ss += vr[k] * vr[k];
+      f = g[n] / sqrtf(ss);
+    }
+    w = kTcScaleW * (scale * (vr[r] * f));
+  }
+  const __half h = __float2half_rn(w);
+  const __half l = __float2half_rn(w - __half2float(h));
+  const int st = n >> 5, kk = n & 31;
+  const size_t off = (size_t)st * kTcStageBytes + (size_t)((r >> 3) * 512 + (r & 7) * 64 + ((((kk >> 3) ^ ((r >> 1) & 3))) << 4) + (kk & 7) * 2);
+  *reinterpret_cast<__half*>(img + off) = h;
+  *reinterpret_cast<__half*>(img + off + 16384) = l;
+}
 
 static int tc_init(hold_ctx*) {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_JVP>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
   return HOLD_OK;
 }
@@ -618,6 +728,7 @@ static void tc_free(NodeState& ns) {
   for (int l = 0; l < HOLD_MAX_LAYERS; ++l) {
     if (ns.tc->sdf_img[l]) cudaFree(ns.tc->sdf_img[l]);
     if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
+    if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
   }
   delete ns.tc;
   ns.tc = nullptr;
@@ -634,6 +745,13 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     if (!t.sdf_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_img[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
     k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  for (int l = 0; l < 8; ++l) {  // W_l^T for the reverse-mode gradient (layers 7..0)
+    const int K_in = (l == 0) ? kEmbed : kHidden, N_out = (l == 3) ? kHidden - kEmbed : kHidden;
+    if (!t.sdf_imgT[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgT[l], (size_t)8 * kTcStageBytes));
+    const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
+    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], N_out, K_in, scale, t.sdf_imgT[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
   for (int l = 0; l < 4; ++l) {
@@ -657,13 +775,27 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
-  if (jvp) {
+  static const bool use_jvp = [] { const char* e = getenv("HOLD_TC_GRAD"); return e != nullptr && strcmp(e, "jvp") == 0; }();
+  if (jvp && !use_jvp) {
+    // reverse mode: 8 forward layers, feature layer, 8 backward layers over the transposed images
+    HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
+    const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
+    void* sig = nullptr;
+    int rc = ws_get(ctx, 12 /* WS_SIG */, (size_t)grid * 8 * kTcRows * 256 * sizeof(float), &sig);
+    if (rc) return rc;
+    a.sig = (float*)sig;
+    a.n_layers = 17;
+    for (int i = 0; i < 8; ++i) {
+      a.L[9 + i].wimg = ns.tc->sdf_imgT[7 - i], a.L[9 + i].bias = nullptr, a.L[9 + i].nst = 8, a.L[9 + i].N = 256;
+    }
+    k_mlp_tc<MLP_SDF_REV><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
+  } else if (jvp) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     int tiles = ceil_div(P, kTcRows / 4);
-    k_mlp_tc<MLP_SDF_JVP><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
   } else {
     int tiles = ceil_div(P, kTcRows);
-    k_mlp_tc<MLP_SDF_ONLY><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
@@ -681,7 +813,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
   a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err;
   int tiles = ceil_div(P, kTcRows);
-  k_mlp_tc<MLP_COLOR><<<tc_grid(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
+  k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }
