@@ -59,51 +59,57 @@ __device__ __forceinline__ void knn15(const float* __restrict__ sv /*smem [778*3
 }
 
 // Same result as knn15 for a point whose neighbour set is probably close to `r`'s current one (the previous sample
-// on the same ray): re-rank the 15 previous neighbours for the new point, which gives a tight upper bound on the
-// 15th distance at once, then scan all vertices — almost every vertex now fails the `dist < worst` test, so the
-// divergent insertion path that dominates knn15 (every warp takes it for most vertices) becomes rare.
-__device__ __forceinline__ void knn15_seeded(const float* __restrict__ sv, float px, float py, float pz, Knn15& r) {
-  int seed[kKnn];
+// on the same ray).  Re-rank the 15 previous neighbours for the new point: their largest distance tau bounds the
+// 15th-nearest distance from above, so the scan over all 778 vertices only has to COLLECT the few vertices below tau
+// (a 2-instruction append to a per-thread list in shared memory) instead of running knn15's divergent sorted
+// insertion for most vertices; the collected candidates are merged afterwards.  Order is lexicographic
+// (distance, index), exactly what knn15 produces.
+constexpr int kKnnCand = 48;
+__device__ __forceinline__ void knn_insert(Knn15& r, float dist, int v) {
+  r.d[kKnn - 1] = dist;
+  r.i[kKnn - 1] = v;
 #pragma unroll
-  for (int k = 0; k < kKnn; ++k) { seed[k] = r.i[k]; r.d[k] = 3.0e38f; }
-#pragma unroll
-  for (int s = 0; s < kKnn; ++s) {
-    const int v = seed[s];
-    float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
-    float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    // sorted insert by (dist, index): the final order must equal a full scan's (ties -> lower index first)
-    r.d[kKnn - 1] = dist;
-    r.i[kKnn - 1] = v;
-#pragma unroll
-    for (int k = kKnn - 1; k > 0; --k) {
-      bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
-      if (sw) {
-        float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
-        int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
-      }
+  for (int k = kKnn - 1; k > 0; --k) {
+    bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
+    if (sw) {
+      float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
+      int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
     }
   }
+}
+__device__ __forceinline__ float knn_dist(const float* __restrict__ sv, int v, float px, float py, float pz) {
+  float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+__device__ __forceinline__ void knn15_seeded(const float* __restrict__ sv, float px, float py, float pz, Knn15& r,
+                                             unsigned short* __restrict__ cand /* smem, [kKnnCand] of this thread */) {
+  int seed[kKnn];
+#pragma unroll
+  for (int k = 0; k < kKnn; ++k) { seed[k] = r.i[k]; r.d[k] = 3.0e38f; r.i[k] = 0x7fffffff; }
+#pragma unroll
+  for (int s = 0; s < kKnn; ++s) knn_insert(r, knn_dist(sv, seed[s], px, py, pz), seed[s]);
+  const float tau = r.d[kKnn - 1];
+  const int itau = r.i[kKnn - 1];
+  int cnt = 0;
   for (int v = 0; v < kVerts; ++v) {
-    float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
-    float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    // candidate iff it would precede the current 15th entry in (dist, index) order
-    if (dist < r.d[kKnn - 1] || (dist == r.d[kKnn - 1] && v < r.i[kKnn - 1])) {
-      bool present = false;
-#pragma unroll
-      for (int k = 0; k < kKnn; ++k) present |= (r.i[k] == v);
-      if (!present) {
-        r.d[kKnn - 1] = dist;
-        r.i[kKnn - 1] = v;
-#pragma unroll
-        for (int k = kKnn - 1; k > 0; --k) {
-          bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
-          if (sw) {
-            float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
-            int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
-          }
-        }
-      }
+    const float dist = knn_dist(sv, v, px, py, pz);
+    if (dist < tau || (dist == tau && v < itau)) {
+      if (cnt < kKnnCand) cand[cnt] = (unsigned short)v;
+      ++cnt;
     }
+  }
+  if (cnt > kKnnCand) {  // seeds were poor (large step along the ray): full scan
+    knn15(sv, px, py, pz, r);
+    return;
+  }
+  for (int c = 0; c < cnt; ++c) {
+    const int v = cand[c];
+    bool present = false;
+#pragma unroll
+    for (int k = 0; k < kKnn; ++k) present |= (r.i[k] == v);
+    if (present) continue;
+    const float dist = knn_dist(sv, v, px, py, pz);
+    if (dist < r.d[kKnn - 1] || (dist == r.d[kKnn - 1] && v < r.i[kKnn - 1])) knn_insert(r, dist, v);
   }
 }
 
@@ -235,7 +241,7 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
 
 // Hand-node variant of k_inverse_warp<true, true> that walks `kSeg` consecutive samples of one ray per thread and
 // seeds each sample's KNN from the previous one (knn15_seeded).  Same arithmetic, same results.
-constexpr int kSeg = 16;
+constexpr int kSeg = 32;
 __global__ void __launch_bounds__(128)
 k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
                          const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
@@ -244,6 +250,8 @@ k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* _
   if (st != nullptr && st->done) return;
   __shared__ float sv[kVerts * 3];
   __shared__ float stf[kJoints * 16];
+  __shared__ unsigned short scand[128 * kKnnCand];
+  unsigned short* cand = scand + threadIdx.x * kKnnCand;
   const int b = blockIdx.y;
   for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
   for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
@@ -261,7 +269,7 @@ k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* _
     const float tz = zbuf[ray * zstride + k];
     const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
     if (k == k0) knn15(sv, x, y, z, nn);
-    else knn15_seeded(sv, x, y, z, nn);
+    else knn15_seeded(sv, x, y, z, nn, cand);
     float T[12], s, dmin;
     blend_tf(nn, skin_w, stf, T, s, dmin);
     float Ai[9];

@@ -64,6 +64,7 @@ struct TcArgs {
   float* rgb;
   const SamplerState* st;
   int* err;
+  int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -309,8 +310,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
               const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
               tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
-              tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
-              tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
+              if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
+              if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
             }
             tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
             if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -397,26 +398,29 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         // layer 4, input of layer 0) collect d sdf/d embed, chained with d embed/d x_c per column.
         float* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
         for (int st = 0; st < 17; ++st) {
-          if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) break;
-          d_par ^= (1u << (st & 1));
-          tc_fence_after();
           const int kind = (st < 8) ? 0 : ((st == 8) ? 1 : ((st < 16) ? 2 : 3));
           const int l = (st <= 8) ? st : 16 - st;
           const float* bias = a.L[st].bias;
+          // per-hand-off side input: bias (forward / feature) or the stashed softplus'(z_{l-1}) (backward), always
+          // requested one hand-off ahead (first one before the accumulator wait)
+          const float* side = (kind <= 1) ? bias : ((kind == 2) ? sig + (size_t)(l - 1) * (kTcRows * 256) : nullptr);
+          float4 nb0 = make_float4(0.f, 0.f, 0.f, 0.f), nb1 = nb0;
+          if (side != nullptr) {
+            nb0 = *reinterpret_cast<const float4*>(side + sub * 8);
+            nb1 = *reinterpret_cast<const float4*>(side + sub * 8 + 4);
+          }
+          if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) break;
+          d_par ^= (1u << (st & 1));
+          tc_fence_after();
           const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 8);
           uint32_t raw[8];
           tc_ld8(t_col, raw);
           for (int h = 0; h < 8; ++h) {
             const int n0 = h * 32 + sub * 8;
-            float bv[8];
-            if (kind <= 1) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
-              bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w, bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
-            } else if (kind == 2) {  // softplus'(z_{l-1}) of this row
-              const float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)(l - 1) * (kTcRows * 256) + n0);
-              const float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)(l - 1) * (kTcRows * 256) + n0 + 4);
-              bv[0] = s0.x, bv[1] = s0.y, bv[2] = s0.z, bv[3] = s0.w, bv[4] = s1.x, bv[5] = s1.y, bv[6] = s1.z, bv[7] = s1.w;
+            const float bv[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
+            if (side != nullptr && h + 1 < 8) {
+              nb0 = *reinterpret_cast<const float4*>(side + n0 + 32);
+              nb1 = *reinterpret_cast<const float4*>(side + n0 + 36);
             }
             tc_wait_ld();
             float acc[8];
@@ -528,17 +532,24 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         const bool head_layer = (MODE == MLP_COLOR) ? (l == a.n_layers - 1) : (l == 7);
         const bool last_mma = (l == a.n_layers - 1);
         const int N = a.L[l].N;
+        const float* bias = a.L[l].bias;
+        float4 nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));      // issued before the wait
+        float4 nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
         if (!mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag)) break;
         d_par ^= (1u << (l & 1));
         tc_fence_after();
-        const float* bias = a.L[l].bias;
         const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
         uint32_t raw[8];
         tc_ld8(t_col, raw);
         for (int h = 0; h < 8; ++h) {
           const int n0 = h * 32 + sub * 8;
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+          // bias of this hand-off was requested one hand-off earlier (L1 is ~0 KB at this smem carve-out: an
+          // un-prefetched __ldg is an L2 round trip on the critical path of every hand-off)
+          const float4 b0 = nb0, b1 = nb1;
+          if (h + 1 < 8) {
+            nb0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32));
+            nb1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32) + 1);
+          }
           const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           tc_wait_ld();
           float acc[8];
@@ -557,8 +568,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             } else if (feat_layer) {
               o = z;
             } else {
-              float e;
-              const float sp = softplus100_fast(z, e);
+              float e = 0.f;
+              const float sp = (a.dbg & 2) ? fmaxf(z, 0.f) * kTcScaleA : softplus100_fast(z, e);
               if (MODE == MLP_SDF_JVP) {
                 // softplus'(z) of the VALUE row (lane & ~3), applied to the tangent rows
                 const float r = mufu_rcp(1.0f + e) * kTcScaleA;   // e = exp(-|100 z|)
@@ -775,6 +786,7 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
+  { const char* e = getenv("HOLD_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
   static const bool use_jvp = [] { const char* e = getenv("HOLD_TC_GRAD"); return e != nullptr && strcmp(e, "jvp") == 0; }();
   if (jvp && !use_jvp) {
     // reverse mode: 8 forward layers, feature layer, 8 backward layers over the transposed images
