@@ -252,8 +252,11 @@ def main():
     k_flops = 2.0 * MAC_SDF_HEAD * P
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     passes = 3 if use_tc else 1
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+    # (profiles/r01_ncu_k_mlp_tc0.md): 414.1 MB + 119.1 MB = the algorithmic 403 MB of x_c in + 134 MB of sdf out.
+    traffic_bytes = 533.2e6 if use_tc else None
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+        "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic_bytes,
         "kernel": "SDF-net launch of one sampler round (262144 x 128 points, sdf head only: 0.918 MFLOP/point algorithmic)",
         "ms_per_launch": k_ms, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, burst: kernel timed alone)",
         "mma_mode": "tcgen05 kind::f16, fp16 hi/lo split x3 passes (fp32-level operands, fp32 accumulate)" if use_tc else "fp32 FFMA on CUDA cores (no tensor pipe)",
