@@ -101,7 +101,9 @@ def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, threads: int | None 
     host cores, in the reference's own 512-ray chunks (datasets/eval_datasets.py:13)."""
     from oracle import hold_oracle as O
 
-    threads = threads or os.cpu_count()
+    # Thread sweep on the round-1 GPU box (2 x Xeon 8562Y+, 128 hw threads), same workload: 16 threads 105 rays/s,
+    # 32: 89, 64: 56, 128: 0.84 (oversubscribed tiny GEMMs).  The baseline uses the best setting, not the most threads.
+    threads = threads or int(os.environ.get("HOLD_CPU_THREADS", min(16, os.cpu_count() or 1)))
     torch.set_num_threads(threads)
     sc2 = make_scene(0)
     g = torch.Generator().manual_seed(11)
@@ -118,7 +120,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = 512
+    n_rays = 2048
     rps, threads, dt = cpu_reference_rays_per_s(n_rays, repeats=max(1, args.steps))
     line = {
         "impl": "reference", "metric": "rays/sec (128 samples/ray)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
@@ -127,7 +129,7 @@ def run_reference(args):
         "config": {"workload": "configs[1]: right hand + rigid object, 512x512 frame, 128 samples/ray (N_eval 128, N 64, extra 32), beta 0.03 -> 5 sampler rounds",
                    "sample": f"{n_rays} rays of the frame per step, 512-ray chunks"},
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_rays} rays x {max(1, args.steps)} steps of the 512x512 workload, torch CPU fp32, {threads} threads"},
+                         "sample": f"{n_rays} rays x {max(1, args.steps)} steps of the 512x512 workload, torch CPU fp32, {threads} threads (best of a 16/32/64/128 sweep)"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,9 +273,10 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rps, threads, dt = cpu_reference_rays_per_s(512, repeats=1)
+        rps, threads, dt = cpu_reference_rays_per_s(2048, repeats=1)
         cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"512 rays (one reference-sized chunk) of the same 512x512 workload in {dt:.1f} s; oracle/hold_oracle.py (torch CPU fp32)"}
+               "sample": f"2048 rays (four reference-sized 512-ray chunks) of the same 512x512 workload in {dt:.1f} s; oracle/hold_oracle.py "
+                         f"(torch CPU fp32, {threads} threads = best of a 16/32/64/128 sweep on this host type)"}
     line = {
         "metric": "rays/sec (128 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
