@@ -10,6 +10,7 @@
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
 #include "composite.cuh"
+#include "background.cuh"
 
 namespace hold {
 
@@ -21,7 +22,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-enum WsSlot { WS_Z = 0, WS_SDF, WS_ZNEW, WS_SDFNEW, WS_BETA, WS_FAR, WS_XC, WS_SSDF, WS_GRAD, WS_FEAT, WS_PE, WS_ZTMP, WS_SIG, WS_COUNT };
+enum WsSlot { WS_Z = 0, WS_SDF, WS_ZNEW, WS_SDFNEW, WS_BETA, WS_FAR, WS_XC, WS_SSDF, WS_GRAD, WS_FEAT, WS_PE, WS_ZTMP, WS_SIG, WS_BGSDF, WS_BGFEAT, WS_BGRGB, WS_COUNT };
 
 int ws_get(hold_ctx* ctx, int slot, size_t bytes, void** out) {
   Buffer& b = ctx->ws[slot];
@@ -182,6 +183,8 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_sampler_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, samp_smem));
   const int mano_smem = (2 * kVerts * 3 + kJoints * 3 + kJoints * 9 + 136 + 2 * kJoints * 16 + 16) * (int)sizeof(float);
   (void)mano_smem;
+  HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_SDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
+  HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
   if (rc) { delete ctx; return rc; }
   *out = ctx;
@@ -206,6 +209,17 @@ int hold_ctx_destroy(hold_ctx* ctx) {
       if (p) cudaFree(p);
     if (ns.sstate) cudaFree(ns.sstate);
     tc_free(ns);
+  }
+  for (int l = 0; l < HOLD_MAX_LAYERS; ++l) {
+    if (ctx->bg_sdf.Wt[l]) cudaFree(ctx->bg_sdf.Wt[l]);
+    if (ctx->bg_sdf.bias[l]) cudaFree(ctx->bg_sdf.bias[l]);
+    if (ctx->bg_rgb.Wt[l]) cudaFree(ctx->bg_rgb.Wt[l]);
+    if (ctx->bg_rgb.bias[l]) cudaFree(ctx->bg_rgb.bias[l]);
+  }
+  {
+    float* ptrs[] = {ctx->bg_sdf.w_last, ctx->bg_sdf.b_last, ctx->bg_rgb.w_last, ctx->bg_rgb.b_last};
+    for (float* p : ptrs)
+      if (p) cudaFree(p);
   }
   if (ctx->dev_err) cudaFree(ctx->dev_err);
   delete ctx;
@@ -580,6 +594,97 @@ int hold_debug_ws_copy(hold_ctx* ctx, int slot, void* dst, size_t bytes) {
   if (!ctx || slot < 0 || slot >= 24 || ctx->ws[slot].bytes < bytes) return HOLD_E_BADARG;
   HOLD_CUDA(cudaDeviceSynchronize());
   HOLD_CUDA(cudaMemcpy(dst, ctx->ws[slot].p, bytes, cudaMemcpyDeviceToDevice));
+  return HOLD_OK;
+}
+
+int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, void* stream) {
+  HOLD_REQUIRE(ctx && sdf && rgb, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  HOLD_REQUIRE(sdf->n_layers == 9 && rgb->n_layers == 2, "background nets: 9 + 2 layers expected");
+  HOLD_REQUIRE(sdf->in_dim[0] == kBgEmbed + kBgFrame, "bg lin0 in_dim %d, expected 116", sdf->in_dim[0]);
+  HOLD_REQUIRE(rgb->in_dim[0] == kBgView + kBgFrame + kFeat && rgb->out_dim[0] == 128 && rgb->out_dim[1] == 3 && rgb->in_dim[1] == 128,
+               "bg colour head must be 315 -> 128 -> 3");
+  PackedMlp& m = ctx->bg_sdf;
+  int rc;
+  for (int l = 0; l < 9; ++l) {
+    const int eo = (l == 3) ? kHidden - kBgEmbed : (l == 8 ? kFeat + 1 : kHidden), ei = (l == 0) ? kBgEmbed + kBgFrame : kHidden;
+    HOLD_REQUIRE(sdf->out_dim[l] == eo && sdf->in_dim[l] == ei, "bg lin%d is %dx%d, expected %dx%d", l, sdf->out_dim[l], sdf->in_dim[l], eo, ei);
+    HOLD_REQUIRE(sdf->weight_v[l] && sdf->bias[l], "bg lin%d has NULL tensors", l);
+    const int K = ei, Kpad = round_up(K, kKC), N = (l == 3) ? kHidden - kBgEmbed : kHidden, row_off = (l == 8) ? 1 : 0;
+    m.K[l] = K, m.N[l] = N, m.Kpad[l] = Kpad, m.Npad[l] = 256;
+    if ((rc = dev_alloc(&m.Wt[l], (size_t)Kpad * 256))) return rc;
+    if ((rc = dev_alloc(&m.bias[l], 256))) return rc;
+    const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
+    k_pack_layer<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->bias[l], sdf->in_dim[l], row_off, 0, K, N, Kpad, scale, m.Wt[l], m.bias[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  m.n_layers = 9;
+  if ((rc = dev_alloc(&m.w_last, 256))) return rc;
+  if ((rc = dev_alloc(&m.b_last, 4))) return rc;
+  k_pack_rows<<<1, 128, 0, s>>>(sdf->weight_v[8], sdf->weight_g[8], sdf->bias[8], 256, 0, 1, m.w_last, m.b_last);
+  HOLD_LAUNCH_CHECK(ctx);
+  PackedMlp& c = ctx->bg_rgb;
+  const int K0 = kBgView + kBgFrame + kFeat, K0pad = round_up(K0, kKC);
+  c.K[0] = K0, c.N[0] = 128, c.Kpad[0] = K0pad, c.Npad[0] = 256;
+  if ((rc = dev_alloc(&c.Wt[0], (size_t)K0pad * 256))) return rc;
+  if ((rc = dev_alloc(&c.bias[0], 256))) return rc;
+  k_pack_layer<<<256, 128, 0, s>>>(rgb->weight_v[0], rgb->weight_g[0], rgb->bias[0], K0, 0, 0, K0, 128, K0pad, 1.0f, c.Wt[0], c.bias[0]);
+  HOLD_LAUNCH_CHECK(ctx);
+  c.n_layers = 2;
+  if ((rc = dev_alloc(&c.w_last, 3 * 128))) return rc;
+  if ((rc = dev_alloc(&c.b_last, 4))) return rc;
+  k_pack_rows<<<3, 128, 0, s>>>(rgb->weight_v[1], rgb->weight_g[1], rgb->bias[1], 128, 0, 3, c.w_last, c.b_last);
+  HOLD_LAUNCH_CHECK(ctx);
+  ctx->has_bg = true;
+  return HOLD_OK;
+}
+
+int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const float* ray_dirs, const float* frame_code,
+                    const float* fg_bg_weights, float* bg_rgb, float* bg_rgb_only, float* bg_semantics, float* bg_z_vals,
+                    void* stream) {
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (!ctx->has_bg) { set_error("background weights not set (hold_bg_set_weights)"); return HOLD_E_STATE; }
+  HOLD_REQUIRE(R >= 0 && B >= 1, "bad R/B");
+  if (R == 0) return HOLD_OK;
+  HOLD_REQUIRE(R % B == 0, "R (%d) must be B (%d) frames x rays, frame-major", R, B);
+  HOLD_REQUIRE(cam_loc && ray_dirs && frame_code && fg_bg_weights, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rpf = R / B;
+  const int rays_per_chunk = max(1, min(rpf, (1 << 20) / kBgN));
+  const size_t cp = (size_t)rays_per_chunk * kBgN;
+  WS(WS_BGSDF, float, cp, sdf_ws);
+  WS(WS_BGFEAT, float, cp * kFeat, feat_ws);
+  WS(WS_BGRGB, float, cp * 3, rgb_ws);
+  for (int b = 0; b < B; ++b) {
+    for (int r0 = 0; r0 < rpf; r0 += rays_per_chunk) {
+      const int rn = min(rays_per_chunk, rpf - r0), P = rn * kBgN;
+      const size_t ray0 = (size_t)b * rpf + r0;
+      BgArgs a;
+      memset(&a, 0, sizeof(a));
+      a.P = P, a.pts_per_frame = P, a.cam = cam_loc + ray0 * 3, a.dirs = ray_dirs + ray0 * 3, a.frame_code = frame_code + (size_t)b * kBgFrame;
+      a.r_sphere = 0.f;
+      // the bounding sphere is a per-node constant in the reference (same value for all nodes): take node 0's
+      for (int n = 0; n < HOLD_MAX_NODES; ++n)
+        if (ctx->nodes[n].configured) { a.r_sphere = ctx->nodes[n].cfg.bounding_sphere; break; }
+      HOLD_REQUIRE(a.r_sphere > 0.f, "configure a node first (scene_bounding_sphere)");
+      a.n_layers = 9;
+      for (int l = 0; l < 9; ++l) { a.L[l].Wt = ctx->bg_sdf.Wt[l], a.L[l].bias = ctx->bg_sdf.bias[l], a.L[l].Kpad = ctx->bg_sdf.Kpad[l], a.L[l].N = ctx->bg_sdf.N[l]; }
+      a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last, a.sdf = sdf_ws, a.feat = feat_ws;
+      const int tiles = ceil_div(P, kTileRows);
+      k_bg_mlp<BG_SDF><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(a);
+      HOLD_LAUNCH_CHECK(ctx);
+      BgArgs c = a;
+      c.n_layers = 1;
+      c.L[0].Wt = ctx->bg_rgb.Wt[0], c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].Kpad = ctx->bg_rgb.Kpad[0], c.L[0].N = 128;
+      c.w_last = ctx->bg_rgb.w_last, c.b_last = ctx->bg_rgb.b_last, c.rgb = rgb_ws;
+      k_bg_mlp<BG_RGB><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(c);
+      HOLD_LAUNCH_CHECK(ctx);
+      k_bg_composite<<<ceil_div(rn, 128), 128, 0, s>>>(rn, a.r_sphere, sdf_ws, rgb_ws, fg_bg_weights + ray0,
+                                                       bg_rgb ? bg_rgb + ray0 * 3 : nullptr, bg_rgb_only ? bg_rgb_only + ray0 * 3 : nullptr,
+                                                       bg_semantics ? bg_semantics + ray0 * 4 : nullptr, bg_z_vals ? bg_z_vals + ray0 * kBgN : nullptr);
+      HOLD_LAUNCH_CHECK(ctx);
+    }
+  }
   return HOLD_OK;
 }
 

@@ -69,6 +69,8 @@ struct hold_ctx {
   int* dev_err = nullptr;
   int64_t launches = 0;
   hold::Buffer ws[24];  // grow-only workspaces, indexed by purpose (api.cu)
+  hold::PackedMlp bg_sdf, bg_rgb;  // background nets (fp32 CUDA-core layout)
+  bool has_bg = false;
 };
 
 namespace hold {

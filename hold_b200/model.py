@@ -265,18 +265,75 @@ class ErrorBoundSampler:
         return z, iters
 
 
+class Background(nn.Module):
+    """model/renderables/background.py:9-165 — the NeRF++ inverted-sphere background.
+    state_dict keys: bg_implicit_network.lin<k>.{weight,bias}, bg_rendering_network.lin<k>.{weight,bias},
+    frame_latent_encoder.weight (the reference's `background.*` keys)."""
+
+    def __init__(self, ctx, num_frames):
+        super().__init__()
+        self.ctx = ctx
+        dims = [84] + [256] * 8 + [257]
+        self.bg_implicit_network = nn.Module()
+        for l in range(9):
+            out = dims[l + 1] - 84 if l + 1 == 4 else dims[l + 1]
+            setattr(self.bg_implicit_network, f"lin{l}", nn.Linear(dims[l] + (32 if l == 0 else 0), out))
+        self.bg_rendering_network = nn.Module()
+        self.bg_rendering_network.lin0 = nn.Linear(315, 128)
+        self.bg_rendering_network.lin1 = nn.Linear(128, 3)
+        self.frame_latent_encoder = nn.Embedding(num_frames, 32)
+
+    def sync_weights(self):
+        isd = dict(self.bg_implicit_network.state_dict())
+        rsd = dict(self.bg_rendering_network.state_dict())
+        wi, k1 = capi.mlp_weights(isd, 9)
+        wr, k2 = capi.mlp_weights(rsd, 2)
+        check(lib().hold_bg_set_weights(self.ctx.h, C.byref(wi), C.byref(wr), stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    @torch.no_grad()
+    def forward(self, bg_weights, ray_dirs, cam_loc, idx, B):
+        """Background.forward + inverse_sample -> dict(bg_rgb, bg_rgb_only, bg_semantics, bg_z_vals)."""
+        R = ray_dirs.shape[0]
+        dev = ray_dirs.device
+        fc = self.frame_latent_encoder(idx).detach().float().contiguous()
+        out = dict(bg_rgb=torch.empty(R, 3, device=dev), bg_rgb_only=torch.empty(R, 3, device=dev),
+                   bg_semantics=torch.empty(R, 4, device=dev), bg_z_vals=torch.empty(R, 32, device=dev))
+        check(lib().hold_background(self.ctx.h, R, B, ptr(cam_loc.float().contiguous()), ptr(ray_dirs.float().contiguous()), ptr(fc),
+                                    ptr(bg_weights.float().contiguous()), ptr(out["bg_rgb"]), ptr(out["bg_rgb_only"]),
+                                    ptr(out["bg_semantics"]), ptr(out["bg_z_vals"]), stream_ptr()))
+        return out
+
+
 class HOLDNet(nn.Module):
     """hold/hold_net.py:23-134, foreground: nodes{right,left,object}; forward_fg(input) -> out dict with the
     reference's keys (fg_rgb, mask_prob, normal, depth, fg_semantics, fg_weights, bg_weights, <node>.*, ray_dirs, cam_loc)."""
 
-    def __init__(self, ctx, nodes: dict):
+    def __init__(self, ctx, nodes: dict, background=None):
         super().__init__()
         self.ctx = ctx
         self.nodes = nn.ModuleDict(nodes)
+        self.background = background
 
     def sync_weights(self):
         for n in self.nodes.values():
             n.sync_weights()
+        if self.background is not None:
+            self.background.sync_weights()
+
+    @torch.no_grad()
+    def forward(self, input):
+        """HOLDNet.forward + composite (hold/hold_net.py:110-134), eval: rgb = fg_rgb + bg_rgb, semantics,
+        bg_rgb_only, instance_map = argmax(semantics)."""
+        out = self.forward_fg(input, return_factors=False)
+        B = input["uv"].shape[0]
+        bg = self.background(out["bg_weights"], out["ray_dirs"], out["cam_loc"], input["idx"], B)
+        out["bg_z_vals"] = bg["bg_z_vals"]
+        out["rgb"] = out["fg_rgb"] + bg["bg_rgb"]
+        out["semantics"] = out["fg_semantics"] + bg["bg_semantics"]
+        out["bg_rgb_only"] = bg["bg_rgb_only"]
+        out["instance_map"] = torch.argmax(out["semantics"], dim=1)
+        return out
 
     @torch.no_grad()
     def forward_fg(self, input, return_factors=True, want_weights=True):

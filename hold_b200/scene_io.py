@@ -8,6 +8,22 @@ from . import capi
 from .model import HOLDNet, Node
 
 
+def build_background(sc, ctx, seed=0):
+    """Background with hold_b200.synth.make_bg_state weights and a seeded frame-code table."""
+    from . import synth
+    from .model import Background
+
+    dev = torch.device("cuda", ctx.device)
+    bg = Background(ctx, sc.B).to(dev)
+    sdf_sd, rgb_sd = synth.make_bg_state(seed)
+    bg.bg_implicit_network.load_state_dict(sdf_sd, strict=True)
+    bg.bg_rendering_network.load_state_dict(rgb_sd, strict=True)
+    g = torch.Generator().manual_seed(5000 + seed)
+    bg.frame_latent_encoder.weight.data.copy_((0.1 * torch.randn(sc.B, 32, generator=g)).to(dev))
+    bg.sync_weights()
+    return bg, sdf_sd, rgb_sd
+
+
 def build_net(sc, ctx, mlp_mode=capi.MLP_FP32):
     dev = torch.device("cuda", ctx.device)
     nodes = {}

@@ -185,6 +185,26 @@ def make_rgb_state(kind: str, seed: int) -> dict:
     return sd
 
 
+def make_bg_state(seed: int) -> tuple[dict, dict]:
+    """Background nets (confs/general.yaml:34-64): ImplicitNet d_in 4 / multires 10 / cond frame(32), init 'none',
+    no weight-norm -> plain `lin<k>.{weight,bias}`; RenderingNet 315 -> 128 -> 3.  Default nn.Linear init."""
+    gen = torch.Generator().manual_seed(4000 + seed)
+
+    def lin(i, o):
+        k = 1.0 / math.sqrt(i)
+        return (torch.rand(o, i, generator=gen) * 2 - 1) * k, (torch.rand(o, generator=gen) * 2 - 1) * k
+
+    dims = [84] + [256] * 8 + [257]
+    sdf, rgb = {}, {}
+    for l in range(9):
+        out_dim = dims[l + 1] - 84 if (l + 1) == 4 else dims[l + 1]
+        in_dim = dims[l] + (32 if l == 0 else 0)
+        sdf[f"lin{l}.weight"], sdf[f"lin{l}.bias"] = lin(in_dim, out_dim)
+    rgb["lin0.weight"], rgb["lin0.bias"] = lin(315, 128)
+    rgb["lin1.weight"], rgb["lin1.bias"] = lin(128, 3)
+    return sdf, rgb
+
+
 # ----------------------------------------------------------------------------- scenes
 
 

@@ -38,7 +38,7 @@ typedef enum hold_status {
 typedef struct hold_ctx hold_ctx;
 
 enum { HOLD_KIND_HAND = 0, HOLD_KIND_OBJECT = 1 };
-/* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 bf16x3 split precision (fp32 accumulate). */
+/* MLP arithmetic: exact fp32 on CUDA cores, or tcgen05 with fp16 hi/lo split operands, 3 passes (fp32 accumulate). */
 enum { HOLD_MLP_FP32 = 0, HOLD_MLP_TC = 1 };
 enum { HOLD_MAX_NODES = 4, HOLD_MAX_LAYERS = 9 };
 
@@ -178,6 +178,18 @@ int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, in
                    const float* ray_dirs, const hold_node_pose* poses /*[n]*/, const hold_factors* factors /*[n]*/,
                    const hold_render_out* comp, const hold_render_out* per_node /*[n] or NULL*/,
                    int32_t* iters /*[n] device*/, void* stream);
+
+/* SURVEY §8f rank 1 — the NeRF++ background (model/renderables/background.py).
+ * hold_bg_set_weights: Background.bg_implicit_network (9 plain layers `lin<k>.{weight,bias}`: weight_g NULL) and
+ * Background.bg_rendering_network (2 plain layers, 315 -> 128 -> 3).
+ * hold_background: HOLDNet.forward's background leg (hold/hold_net.py:91-118,125-134): inverse_sample +
+ * Background.forward.  fg_bg_weights [R] is volumetric_render's `bg_weights`; frame_code [B,32] is
+ * Background.frame_latent_encoder(idx).  Outputs (any may be NULL): bg_rgb [R,3] (= bg_weights * bg_rgb_only),
+ * bg_rgb_only [R,3], bg_semantics [R,4], bg_z_vals [R,32]. */
+int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, void* stream);
+int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const float* ray_dirs, const float* frame_code,
+                    const float* fg_bg_weights, float* bg_rgb, float* bg_rgb_only, float* bg_semantics,
+                    float* bg_z_vals, void* stream);
 
 /* Building blocks exported for tests and for callers that hold canonical points already
  * (hold_utils.query_oc, meshing): ImplicitNet.forward on canonical points (shape_net.py:84-130). */

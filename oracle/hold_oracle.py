@@ -587,3 +587,83 @@ def render_scene(sc, ray_ids=None, chunk=None, trace=None, stable_ties=False):
         comp = composite(fl, stable_ties)
         outs.append(dict(nodes=fl, render=comp))
     return outs, art
+
+
+# ----------------------------------------------------------------------------- §8f rank 1: NeRF++ background
+
+
+def embed_n(x, n_freq):
+    """engine/embedders.py:48-51 for any input width (background: 4-d points x 10 freqs, view dirs x 4 freqs)."""
+    out = [x]
+    for k in range(n_freq):
+        f = float(2.0**k)
+        out += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(out, -1)
+
+
+def bg_sdf_mlp(p4, frame_code, sd):
+    """Background ImplicitNet (confs/general.yaml:34-54): d_in 4, multires 10 (84), cond 'frame' (32) at layer 0,
+    8x256, skip_in [4], no weight-norm, Softplus(100).  p4 [P,4], frame_code [P,32] -> [P,257]."""
+    e = embed_n(p4, 10)
+    h = e
+    for l in range(9):
+        if l == 0:
+            h = torch.cat([h, frame_code], -1)
+        if l == 4:
+            h = torch.cat([h, e], 1) / math.sqrt(2)
+        h = F.linear(h, sd[f"lin{l}.weight"], sd[f"lin{l}.bias"])
+        if l < 8:
+            h = F.softplus(h, beta=100)
+    return h
+
+
+def bg_rgb_mlp(view_dirs, frame_code, feat, sd):
+    """Background RenderingNet, mode 'nerf_frame_encoding' (texture_net.py:55-68,93-101; general.yaml:55-64)."""
+    h = torch.cat([embed_n(view_dirs, 4), frame_code, feat], -1)
+    h = torch.relu(F.linear(h, sd["lin0.weight"], sd["lin0.bias"]))
+    return torch.sigmoid(F.linear(h, sd["lin1.weight"], sd["lin1.bias"]))
+
+
+def depth2pts_outside(ray_o, ray_d, depth, R_s):
+    """Background.depth2pts_outside, model/renderables/background.py:102-135 (NeRF++ inverted sphere)."""
+    o_dot_d = torch.sum(ray_d * ray_o, dim=-1)
+    under = o_dot_d**2 - ((ray_o**2).sum(-1) - R_s**2)
+    d_sphere = torch.sqrt(under) - o_dot_d
+    p_sphere = ray_o + d_sphere.unsqueeze(-1) * ray_d
+    p_mid = ray_o - o_dot_d.unsqueeze(-1) * ray_d
+    p_mid_norm = torch.norm(p_mid, dim=-1)
+    axis = torch.cross(ray_o, p_sphere, dim=-1)
+    axis = axis / torch.norm(axis, dim=-1, keepdim=True)
+    phi = torch.asin(p_mid_norm / R_s)
+    theta = torch.asin(p_mid_norm * depth)
+    ang = (phi - theta).unsqueeze(-1)
+    pn = (p_sphere * torch.cos(ang) + torch.cross(axis, p_sphere, dim=-1) * torch.sin(ang)
+          + axis * torch.sum(axis * p_sphere, dim=-1, keepdim=True) * (1.0 - torch.cos(ang)))
+    pn = pn / torch.norm(pn, dim=-1, keepdim=True)
+    return torch.cat((pn, depth.unsqueeze(-1)), dim=-1)
+
+
+def background(bg_weights, ray_dirs, cam_loc, frame_code, frame_of_ray, bg_sdf_sd, bg_rgb_sd, R_s, n_bg=32):
+    """HOLDNet.forward's background leg (hold_net.py:91-118) = inverse_sample (ray_sampler.py:82-85) +
+    Background.forward (background.py:35-100) + bg_volume_rendering (:137-165).  Eval mode.
+    Returns bg_rgb [R,3], bg_rgb_only [R,3], bg_semantics [R,4], z_bg [R,n_bg]."""
+    R = ray_dirs.shape[0]
+    z_bg = uniform_z(0.0, torch.ones(R, 1), n_bg) * (1.0 / R_s)
+    zf = torch.flip(z_bg, dims=[-1])
+    dirs = ray_dirs.unsqueeze(1).repeat(1, n_bg, 1)
+    locs = cam_loc.unsqueeze(1).repeat(1, n_bg, 1)
+    p4 = depth2pts_outside(locs, dirs, zf, R_s).reshape(-1, 4)
+    fc = frame_code[frame_of_ray].repeat_interleave(n_bg, 0)
+    o = bg_sdf_mlp(p4, fc, bg_sdf_sd)
+    sdf, feat = o[:, :1], o[:, 1:]
+    rgb = bg_rgb_mlp(dirs.reshape(-1, 3), fc, feat, bg_rgb_sd).reshape(R, n_bg, 3)
+    dens = sdf.abs().reshape(R, n_bg)                                  # AbsDensity, engine/density.py:33-35
+    d = torch.cat([zf[:, :-1] - zf[:, 1:], torch.full((R, 1), 1e10)], -1)
+    fe = d * dens
+    alpha = 1 - torch.exp(-fe)
+    T = torch.exp(-torch.cumsum(torch.cat([torch.zeros(R, 1), fe[:, :-1]], -1), -1))
+    w = alpha * T
+    only = (w.unsqueeze(-1) * rgb).sum(1)
+    sem = torch.zeros(R, 4)
+    sem[:, 0] = 1.0
+    return bg_weights.unsqueeze(-1) * only, only, bg_weights.unsqueeze(-1) * sem, z_bg

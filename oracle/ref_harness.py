@@ -285,7 +285,42 @@ def check():
                 ok &= _cmp(f"{nid}.render.{key}", oo[0]["render"][k][key], ro[0]["render"][k][key], 1e-4)
         for key in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
             ok &= _cmp(f"comp.{key}", oo[0]["render"]["comp"][key], ro[0]["render"]["comp"][key], 1e-4)
+    ok &= check_background()
     print("ORACLE == REFERENCE" if ok else "ORACLE != REFERENCE")
+    return ok
+
+
+def check_background():
+    """oracle.background vs the reference's Background class (model/renderables/background.py)."""
+    from hold_b200 import synth
+    from oracle import hold_oracle as O
+    from src.model.renderables.background import Background
+
+    opt = ns(bg_implicit_network=ns(feature_vector_size=256, d_in=4, d_out=1, dims=[256] * 8, init="none", bias=0.0, skip_in=[4],
+                                    weight_norm=False, multires=10, cond="frame", dim_frame_encoding=32),
+             bg_rendering_network=ns(feature_vector_size=256, mode="nerf_frame_encoding", d_in=3, d_out=3, dims=[128],
+                                     weight_norm=False, multires_view=4, dim_frame_encoding=32))
+    bg = Background(opt, ns(barf_s=0, barf_e=10, no_barf=False), 3, 6.0)
+    sdf_sd, rgb_sd = synth.make_bg_state(0)
+    bg.bg_implicit_network.load_state_dict(sdf_sd, strict=False)
+    bg.bg_rendering_network.load_state_dict(rgb_sd, strict=False)
+    bg.eval()
+    sc = synth.make_scene(H=8, W=8, S=32, B=2)
+    sc.intrinsics[:, 0, 2] += 0.37   # a ray through the sphere centre is a 0/0 in depth2pts_outside (background.py:118-119)
+    sc.intrinsics[:, 1, 2] -= 0.21
+    from oracle.hold_oracle import camera_rays
+    dirs, cam = camera_rays(sc.uv, sc.extrinsics, sc.intrinsics)
+    P = dirs.shape[1]
+    dirs, cam = dirs.reshape(-1, 3), cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3)
+    bgw = torch.rand(dirs.shape[0], generator=torch.Generator().manual_seed(0))
+    idx = torch.tensor([2, 0])
+    zbg = bg.inverse_sphere_sampler.inverse_sample(dirs, cam, False, 6.0)
+    with torch.no_grad():
+        ref = bg(bgw, dirs, cam, zbg, idx)
+        o = O.background(bgw, dirs, cam, bg.frame_latent_encoder.weight.data[idx], torch.arange(2).repeat_interleave(P), sdf_sd, rgb_sd, 6.0)
+    print("[background]")
+    ok = _cmp("bg_rgb", o[0], ref["bg_rgb"], 1e-6) & _cmp("bg_rgb_only", o[1], ref["bg_rgb_only"], 1e-6)
+    ok &= _cmp("bg_semantics", o[2], ref["bg_semantics"], 1e-6) & _cmp("bg_z_vals", o[3], zbg, 1e-7)
     return ok
 
 
