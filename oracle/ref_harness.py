@@ -290,10 +290,10 @@ def check():
     return ok
 
 
-def check_background():
-    """oracle.background vs the reference's Background class (model/renderables/background.py)."""
+def _bg_case():
+    """A background case: seeded inputs + the REFERENCE Background class's outputs (model/renderables/background.py)."""
     from hold_b200 import synth
-    from oracle import hold_oracle as O
+    from oracle.hold_oracle import camera_rays
     from src.model.renderables.background import Background
 
     opt = ns(bg_implicit_network=ns(feature_vector_size=256, d_in=4, d_out=1, dims=[256] * 8, init="none", bias=0.0, skip_in=[4],
@@ -308,7 +308,6 @@ def check_background():
     sc = synth.make_scene(H=8, W=8, S=32, B=2)
     sc.intrinsics[:, 0, 2] += 0.37   # a ray through the sphere centre is a 0/0 in depth2pts_outside (background.py:118-119)
     sc.intrinsics[:, 1, 2] -= 0.21
-    from oracle.hold_oracle import camera_rays
     dirs, cam = camera_rays(sc.uv, sc.extrinsics, sc.intrinsics)
     P = dirs.shape[1]
     dirs, cam = dirs.reshape(-1, 3), cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3)
@@ -317,11 +316,33 @@ def check_background():
     zbg = bg.inverse_sphere_sampler.inverse_sample(dirs, cam, False, 6.0)
     with torch.no_grad():
         ref = bg(bgw, dirs, cam, zbg, idx)
-        o = O.background(bgw, dirs, cam, bg.frame_latent_encoder.weight.data[idx], torch.arange(2).repeat_interleave(P), sdf_sd, rgb_sd, 6.0)
+    inp = dict(bg_weights=bgw, ray_dirs=dirs, cam_loc=cam, frame_code=bg.frame_latent_encoder.weight.data[idx].clone(),
+               frame_of_ray=torch.arange(2).repeat_interleave(P), r_sphere=6.0, bg_state_seed=0)
+    out = dict(bg_rgb=ref["bg_rgb"], bg_rgb_only=ref["bg_rgb_only"], bg_semantics=ref["bg_semantics"], bg_z_vals=zbg)
+    return inp, out, (sdf_sd, rgb_sd)
+
+
+def check_background():
+    """oracle.background vs the reference's Background class."""
+    from oracle import hold_oracle as O
+
+    inp, ref, (sdf_sd, rgb_sd) = _bg_case()
+    o = O.background(inp["bg_weights"], inp["ray_dirs"], inp["cam_loc"], inp["frame_code"], inp["frame_of_ray"], sdf_sd, rgb_sd, 6.0)
     print("[background]")
     ok = _cmp("bg_rgb", o[0], ref["bg_rgb"], 1e-6) & _cmp("bg_rgb_only", o[1], ref["bg_rgb_only"], 1e-6)
-    ok &= _cmp("bg_semantics", o[2], ref["bg_semantics"], 1e-6) & _cmp("bg_z_vals", o[3], zbg, 1e-7)
+    ok &= _cmp("bg_semantics", o[2], ref["bg_semantics"], 1e-6) & _cmp("bg_z_vals", o[3], ref["bg_z_vals"], 1e-7)
     return ok
+
+
+def golden_background():
+    """tests/golden/background/*.pt: inputs + the reference Background class's outputs."""
+    inp, ref, _ = _bg_case()
+    d = os.path.join(REPO, "tests", "golden", "background")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "bg_8x8_B2.pt")
+    torch.save({"in": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()},
+                "out": {k: v.detach().clone() for k, v in ref.items()}}, path)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
 def golden():
@@ -366,3 +387,5 @@ if __name__ == "__main__":
         sys.exit(0 if check() else 1)
     elif cmd == "golden":
         golden()
+    elif cmd == "golden_background":
+        golden_background()

@@ -74,3 +74,19 @@ def test_oracle_edge_cases():
     p, v = torch.rand(7, 3), torch.rand(50, 3)
     dd, ii = O.knn_points(p, v, 15)
     assert (dd[:, 1:] >= dd[:, :-1]).all() and torch.allclose(dd, ((p[:, None] - v[ii]) ** 2).sum(-1))
+
+
+def test_background_oracle_matches_reference_golden():
+    """oracle.background against outputs of the reference's Background class
+    (oracle/ref_harness.py golden_background)."""
+    import torch
+    from hold_b200 import synth
+    from oracle import hold_oracle as O
+
+    rec = torch.load(os.path.join(os.path.dirname(__file__), "golden", "background", "bg_8x8_B2.pt"))
+    i, ref = rec["in"], rec["out"]
+    sdf_sd, rgb_sd = synth.make_bg_state(i["bg_state_seed"])
+    o = O.background(i["bg_weights"], i["ray_dirs"], i["cam_loc"], i["frame_code"], i["frame_of_ray"], sdf_sd, rgb_sd, i["r_sphere"])
+    for got, key in zip(o, ("bg_rgb", "bg_rgb_only", "bg_semantics", "bg_z_vals")):
+        assert torch.isfinite(ref[key]).all()
+        assert (got - ref[key]).abs().max().item() <= 2e-6, key

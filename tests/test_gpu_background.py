@@ -44,3 +44,32 @@ def test_background_and_full_composite(ctx):
     ob = O.background(r["bg_weights"], dirs, cam, fc, frame, sdf_sd, rgb_sd, sc.bounding_sphere)
     d = (out["rgb"].cpu() - (r["fg_rgb"] + ob[0])).abs()
     assert d.mean().item() <= 8e-3 and d.max().item() <= 1.5e-1
+
+
+def test_background_against_reference_golden(ctx):
+    """hold_background against the committed outputs of the reference's own Background class."""
+    import os
+    from hold_b200 import capi, synth
+    from hold_b200.capi import check, lib, ptr, stream_ptr
+    import ctypes as C
+
+    rec = torch.load(os.path.join(os.path.dirname(__file__), "golden", "background", "bg_8x8_B2.pt"))
+    i, ref = rec["in"], rec["out"]
+    dev = torch.device("cuda", 0)
+    sc = synth.make_scene(H=8, W=8, S=32, B=2)
+    from hold_b200 import scene_io
+    scene_io.build_net(sc, ctx, capi.MLP_FP32)  # configures a node: the bounding sphere comes from it
+    sdf_sd, rgb_sd = synth.make_bg_state(i["bg_state_seed"])
+    wi, k1 = capi.mlp_weights({k: v.to(dev) for k, v in sdf_sd.items()}, 9)
+    wr, k2 = capi.mlp_weights({k: v.to(dev) for k, v in rgb_sd.items()}, 2)
+    check(lib().hold_bg_set_weights(ctx.h, C.byref(wi), C.byref(wr), stream_ptr()))
+    R = i["ray_dirs"].shape[0]
+    t = {k: i[k].to(dev).float().contiguous() for k in ("cam_loc", "ray_dirs", "frame_code", "bg_weights")}
+    out = dict(bg_rgb=torch.empty(R, 3, device=dev), bg_rgb_only=torch.empty(R, 3, device=dev),
+               bg_semantics=torch.empty(R, 4, device=dev), bg_z_vals=torch.empty(R, 32, device=dev))
+    check(lib().hold_background(ctx.h, R, 2, ptr(t["cam_loc"]), ptr(t["ray_dirs"]), ptr(t["frame_code"]), ptr(t["bg_weights"]),
+                                ptr(out["bg_rgb"]), ptr(out["bg_rgb_only"]), ptr(out["bg_semantics"]), ptr(out["bg_z_vals"]), stream_ptr()))
+    ctx.check()
+    for k, v in out.items():
+        err = (v.cpu() - ref[k]).abs().max().item()
+        assert err <= 1e-5, f"{k}: {err:.2e}"
