@@ -9,6 +9,7 @@
 #include "sampler.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc2.cuh"
 #include "composite.cuh"
 #include "background.cuh"
 
@@ -77,7 +78,7 @@ static int launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, cons
                       float* grad, float* feat, const SamplerState* st, cudaStream_t s) {
   if (P <= 0) return HOLD_OK;
   const bool jvp = (grad != nullptr) || (feat != nullptr);
-  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
+  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc2_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
   SimtArgs a;
   memset(&a, 0, sizeof(a));
   fill_sdf_args(ns, a, jvp);
@@ -186,6 +187,7 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_SDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
+  if (rc == HOLD_OK) rc = tc2_init();
   if (rc) { delete ctx; return rc; }
   *out = ctx;
   return HOLD_OK;
