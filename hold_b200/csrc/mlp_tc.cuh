@@ -64,7 +64,9 @@ struct TcArgs {
   float* rgb;
   const SamplerState* st;
   int* err;
-  int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too
+  int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too,
+            // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel)
+  long long* prof;  // pair kernel, HOLD_TC_PROF=1: cycle accounting of cluster 0 (see mlp_tc2.cuh)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -130,6 +132,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a fully converged warp.  The single-thread roles (bulk copies, tcgen05.mma / commit) run their loops
+// with ALL lanes and elect the issuing lane per instruction group: with warp-uniform control flow the compiler keeps
+// descriptors and barrier addresses in uniform registers; inside an `if (lane == 0)` region it wraps every UTCHMMA /
+// UTCBAR / UBLKCP in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~25 instructions each), which made the issuer
+// thread the bottleneck of the whole kernel (~1 k clk of issue overhead per weight stage).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // UMMA shared-memory descriptor, K-major canonical layouts (cute/arch/mma_sm100_desc.hpp semantics):
 // start address >> 4 | LBO (=1, unused for swizzled K-major) | SBO = bytes between 8-row groups | version 1 | layout
@@ -271,37 +287,46 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
 
   if (warp == 0) {
     // ============================================================ weight producer (TMA engine, bulk async copies)
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < a.n_layers; ++l) {
           const uint8_t* src = a.L[l].wimg;
           for (int s = 0; s < a.L[l].nst; ++s) {
-            if (!mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag)) goto tc_done;
-            mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
-            bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
+            if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto tc_done;
+            if (elect_one()) {
+              if (a.dbg & 8) {
+                mbar_arrive(bWFull + 8 * stage);
+              } else {
+                mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
+                bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
+              }
+            }
+            __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp walks the loop, one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
       uint32_t a_par = 0;  // bit c = parity to wait for on a_ready[c]
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < a.n_layers; ++l) {
-          const uint32_t d_tmem = tmem + (uint32_t)((l & 1) * 256);
+          const uint32_t d_tmem = tmem_u + (uint32_t)((l & 1) * 256);
           const int nst = a.L[l].nst;
           for (int s = 0; s < nst; ++s) {
             const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
-            if (!mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag)) goto tc_done;  // hand-off s = columns [32 s, 32 s + 32)
+            // hand-off s = columns [32 s, 32 s + 32) of the previous layer's activations
+            if (!__all_sync(0xffffffffu, mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag))) goto tc_done;
             a_par ^= (1u << s);
-            tc_fence_after();
-            if (!mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag)) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag))) goto tc_done;
             tc_fence_after();
             const uint32_t wb = sW + stage * kTcStageBytes;
+            const bool el = elect_one();
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
@@ -309,14 +334,18 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
               const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
               const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
-              tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
-              if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
-              if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
+              if (el) {
+                tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
+                if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
+                if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
+              }
             }
-            tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
+            if (el) tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
+            __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bDFull + 8 * (l & 1));  // accumulator of layer l complete
+          if (elect_one()) tc_commit(bDFull + 8 * (l & 1));  // accumulator of layer l complete
+          __syncwarp();
         }
       }
     }

@@ -71,6 +71,15 @@ __device__ __forceinline__ bool mbar_wait2(uint32_t bar, uint32_t parity, int* e
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer), "r"(1u) : "memory");
   return false;
 }
+// the same, adding the cycles spent to `acc` when profiling is on (HOLD_TC_PROF=1, cluster 0 only)
+__device__ __forceinline__ bool mbar_wait2t(uint32_t bar, uint32_t parity, int* err, int tag, volatile int* abort_flag, bool prof,
+                                            long long& acc) {
+  if (!prof) return mbar_wait2(bar, parity, err, tag, abort_flag);
+  const long long t0 = clock64();
+  const bool ok = mbar_wait2(bar, parity, err, tag, abort_flag);
+  acc += clock64() - t0;
+  return ok;
+}
 // completion of all previously issued MMAs -> one arrival on the barrier at the same smem offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit2(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -95,33 +104,34 @@ struct T2Epi {            // per-thread constants of an epilogue warp
   uint32_t t_lane;        // TMEM address of this warp's lane quarter, column 0
   uint8_t* gA;            // generic pointer to the A region (tile X hi | X lo | Y hi | Y lo)
   const float* bias;      // smem: [9][256], layers 0..7 pre-multiplied by 64
-  uint32_t a_ready;       // shared::cluster address of the leader's a_ready[2][8]
+  uint32_t a_ready;       // shared::cluster address of the leader's a_ready[2][4]
   uint32_t d_full;        // local d_full[2][2]
   volatile int* abort_flag;
   int row, qh, sub, lane; // row 0..63 inside the CTA's half tile; qh = column half; sub = warp of the quarter
+  bool prof;
 };
 
-__device__ __forceinline__ void t2_store_a(const T2Epi& e, int t, int n0, const float (&out)[8]) {
+__device__ __forceinline__ void t2_store_a(const T2Epi& e, int t, int n0, int round, const float (&out)[8]) {
   uint4 hi, lo;
   split8(out, hi, lo);
   const int c64 = n0 >> 6, ju = (n0 & 63) >> 3;
   const uint32_t off = (uint32_t)(t * kT2ATile + c64 * 8192 + (e.row >> 3) * 1024 + (e.row & 7) * 128 + ((ju ^ (e.row & 7)) << 4));
   *reinterpret_cast<uint4*>(e.gA + off) = hi;
   *reinterpret_cast<uint4*>(e.gA + off + kT2APart) = lo;
-  // one arrival per warp on the leader's hand-off barrier of k-chunk n0 / 32 of tile t
+  // one arrival per warp on the leader's hand-off barrier of this round (k-chunks j and 4 + j) of tile t
   fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (e.lane == 0) mbar_arrive_cluster(e.a_ready + 8 * (t * 8 + (n0 >> 5)));
+  if (e.lane == 0) mbar_arrive_cluster(e.a_ready + 8 * (t * 4 + round));
 }
 
 // One (tile, step) of the epilogue.  KIND 0: forward layer l (softplus; REV: stash softplus'); 1: feature layer +
 // start of the backward chain; 2: backward through layer l; 3: backward through layer 0 (embedding derivative).
 template <int MODE, int KIND>
 __device__ __forceinline__ bool t2_epi(const TcArgs& a, const T2Epi& e, int t, int step, int l, bool store_a, float px, float py,
-                                       float pz, bool valid, int p, float& h0, float& h1, float& h2, float& h3, uint32_t& d_par) {
+                                       float pz, bool valid, int p, float& h0, float& h1, float& h2, float& h3, uint32_t& d_par, long long& t_wait) {
   const int di = t * 2 + (step & 1);
-  if (!mbar_wait2(e.d_full + 8 * di, (d_par >> di) & 1, a.err, 4, e.abort_flag)) return false;
+  if (!mbar_wait2t(e.d_full + 8 * di, (d_par >> di) & 1, a.err, 4, e.abort_flag, e.prof, t_wait)) return false;
   d_par ^= (1u << di);
   tc_fence_after();
   const uint32_t t_col = e.t_lane + (uint32_t)(di * 128 + e.sub * 8);
@@ -156,9 +166,14 @@ __device__ __forceinline__ bool t2_epi(const TcArgs& a, const T2Epi& e, int t, i
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float z64 = fmaf(acc[i], kT2AccToZ64, sv[i]);
-        const float u = mufu_ex2(-fabsf(z64 * kT2Z64ToT));
-        const float L = mufu_lg2(1.0f + u);
-        out[i] = fmaf(L, kT2LgToOut, fmaxf(z64, 0.f));
+        float u = 0.f;
+        if (a.dbg & 2) {
+          out[i] = fmaxf(z64, 0.f);
+        } else {
+          u = mufu_ex2(-fabsf(z64 * kT2Z64ToT));
+          const float L = mufu_lg2(1.0f + u);
+          out[i] = fmaf(L, kT2LgToOut, fmaxf(z64, 0.f));
+        }
         if (MODE == MLP_SDF_REV) {
           const float r = mufu_rcp(1.0f + u);
           sg[i] = (z64 >= 0.f) ? r : u * r;
@@ -224,7 +239,7 @@ __device__ __forceinline__ bool t2_epi(const TcArgs& a, const T2Epi& e, int t, i
         }
       }
     }
-    if (KIND != 3 && store_a) t2_store_a(e, t, n0, out);
+    if (KIND != 3 && store_a) t2_store_a(e, t, n0, j, out);
   }
   return true;
 }
@@ -238,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sW = base + kT2SmemA, sBias = sW + kT2SmemW, sBar = sBias + kT2SmemBias;
-  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bWPeer = sBar + 16 * NS, bAReady = sBar + 24 * NS, bDFull = bAReady + 128;
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 64;
   const uint32_t sTmemPtr = bDFull + 32, sAbort = sTmemPtr + 4;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,11 +261,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
   const int n_super = ceil_div(a.P, 2 * kT2TilePts);
   const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const bool prof = (a.prof != nullptr) && (cluster_id == 0);
+  const uint32_t ns_eff = (a.dbg & 16) ? 3u : (uint32_t)NS;
+  long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;  // profiling accumulators of this thread
+  const long long t_begin = prof ? clock64() : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); mbar_init(bWPeer + 8 * i, 1); }
+    // leader's w_full: its own expect_tx arrival + the peer's forwarded "my half has landed"
+    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, rank == 0 ? 2 : 1); mbar_init(bWEmpty + 8 * i, 1); }
     *abort_flag = 0;
-    for (int i = 0; i < 16; ++i) mbar_init(bAReady + 8 * i, 16);  // 8 epilogue warps of each CTA feed one k-chunk
+    for (int i = 0; i < 8; ++i) mbar_init(bAReady + 8 * i, 32);  // a_ready[tile][round]: all 16 epilogue warps of both CTAs
     for (int i = 0; i < 4; ++i) mbar_init(bDFull + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -274,7 +294,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
 
   if (warp == 0) {
     // ============================================================ weight producer: this CTA's half of every stage
-    if (lane == 0) {
+    // (all lanes walk the loops, one elected lane issues: see elect_one() in mlp_tc.cuh)
+    {
       uint32_t stage = 0, phase = 0;
       for (int su = cluster_id; su < n_super; su += n_clusters) {
         for (int step = 0; step < NSTEP; ++step) {
@@ -283,48 +304,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
           for (int t = 0; t < 2; ++t) {
             for (int si = 0; si < nst; ++si) {
               const int c = (nst == 8) ? ((si >> 1) + 4 * (si & 1)) : si;
-              if (!mbar_wait2(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag)) goto tc2_done;
-              mbar_expect_tx(bWFull + 8 * stage, kT2HalfStage);
-              bulk_g2s(sW + stage * kT2HalfStage, src + (size_t)c * kTcStageBytes, 8192, bWFull + 8 * stage);
-              bulk_g2s(sW + stage * kT2HalfStage + 8192, src + (size_t)c * kTcStageBytes + 16384, 8192, bWFull + 8 * stage);
-              if (++stage == NS) { stage = 0; phase ^= 1; }
+              if (!__all_sync(0xffffffffu, mbar_wait2t(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag, prof, tp0))) goto tc2_done;
+              if (elect_one()) {
+                if (a.dbg & 8) {
+                  mbar_arrive(bWFull + 8 * stage);
+                } else {
+                  mbar_expect_tx(bWFull + 8 * stage, kT2HalfStage);
+                  bulk_g2s(sW + stage * kT2HalfStage, src + (size_t)c * kTcStageBytes, 8192, bWFull + 8 * stage);
+                  bulk_g2s(sW + stage * kT2HalfStage + 8192, src + (size_t)c * kTcStageBytes + 16384, 8192, bWFull + 8 * stage);
+                }
+              }
+              __syncwarp();
+              if (++stage == ns_eff) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
+      if (prof && lane == 0) { a.prof[8 + 2 * rank] = clock64() - t_begin; a.prof[9 + 2 * rank] = tp0; }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 1) {
-      // ========================================================== peer: forward "my half has landed" to the leader
+    if (rank == 1) {
+      // ========================================================== peer: forward "my half has landed" to the leader's w_full
       uint32_t stage = 0, phase = 0;
-      const uint32_t peer_bar = mapa_rank(bWPeer, 0);
+      const uint32_t leader_full = mapa_rank(bWFull, 0);
       for (int su = cluster_id; su < n_super; su += n_clusters)
         for (int step = 0; step < NSTEP; ++step)
           for (int k = 0; k < 2 * a.L[step].nst; ++k) {
-            if (!mbar_wait2(bWFull + 8 * stage, phase, a.err, 5, abort_flag)) goto tc2_done;
-            mbar_arrive_cluster(peer_bar + 8 * stage);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
+            if (!__all_sync(0xffffffffu, mbar_wait2t(bWFull + 8 * stage, phase, a.err, 5, abort_flag, prof, tp0))) goto tc2_done;
+            if (elect_one()) mbar_arrive_cluster(leader_full + 8 * stage);
+            __syncwarp();
+            if (++stage == ns_eff) { stage = 0; phase ^= 1; }
           }
-    }
-    if (lane == 0 && rank == 0) {
+      if (prof && lane == 0) a.prof[12] = tp0;
+    } else {
       // ========================================================== leader: MMA issuer for the pair
       uint32_t stage = 0, phase = 0;
-      uint32_t a_par = 0;  // bit t*8+c = parity to wait for on a_ready[t][c]
+      uint32_t a_par = 0;  // bit t*4+j = parity to wait for on a_ready[t][j]
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       for (int su = cluster_id; su < n_super; su += n_clusters) {
         for (int step = 0; step < NSTEP; ++step) {
           const int nst = a.L[step].nst;
           for (int t = 0; t < 2; ++t) {
-            const uint32_t d_tmem = tmem + (uint32_t)((t * 2 + (step & 1)) * 128);
+            const uint32_t d_tmem = tmem_u + (uint32_t)((t * 2 + (step & 1)) * 128);
             const uint32_t aT = sA + t * kT2ATile;
             for (int si = 0; si < nst; ++si) {
               const int c = (nst == 8) ? ((si >> 1) + 4 * (si & 1)) : si;
-              const int bi = t * 8 + c;
-              if (!mbar_wait2(bAReady + 8 * bi, (a_par >> bi) & 1, a.err, 2, abort_flag)) goto tc2_done;
-              a_par ^= (1u << bi);
-              if (!mbar_wait2(bWFull + 8 * stage, phase, a.err, 3, abort_flag)) goto tc2_done;
-              if (!mbar_wait2(bWPeer + 8 * stage, phase, a.err, 6, abort_flag)) goto tc2_done;
+              if ((si & 1) == 0) {  // one hand-off barrier per epilogue round: chunks j and 4 + j (layer 0: chunks 0, 1)
+                const int bi = t * 4 + (si >> 1);
+                if (!__all_sync(0xffffffffu, mbar_wait2t(bAReady + 8 * bi, (a_par >> bi) & 1, a.err, 2, abort_flag, prof, tp1))) goto tc2_done;
+                a_par ^= (1u << bi);
+              }
+              // own half (expect_tx + bytes) and the peer's forwarded arrival complete the same barrier
+              if (!__all_sync(0xffffffffu, mbar_wait2t(bWFull + 8 * stage, phase, a.err, 3, abort_flag, prof, tp2))) goto tc2_done;
               tc_fence_after();
               const uint32_t wb = sW + stage * kT2HalfStage;
+              const bool el = elect_one();
 #pragma unroll
               for (int jj = 0; jj < 2; ++jj) {
                 const uint32_t koff = (uint32_t)(((c & 1) * 2 + jj) * 32);  // bytes inside the 128-byte A row
@@ -332,17 +366,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
                 const uint64_t alo = umma_desc(aT + kT2APart + (c >> 1) * 8192 + koff, 1024, kLayoutSW128);
                 const uint64_t whi = umma_desc(wb + jj * 32, 512, kLayoutSW64);
                 const uint64_t wlo = umma_desc(wb + 8192 + jj * 32, 512, kLayoutSW64);
-                tc_mma2(d_tmem, ahi, whi, kIdescBf16, (si | jj) != 0);
-                tc_mma2(d_tmem, alo, whi, kIdescBf16, 1);
-                tc_mma2(d_tmem, ahi, wlo, kIdescBf16, 1);
+                if (el) {
+                  tc_mma2(d_tmem, ahi, whi, kIdescBf16, (si | jj) != 0);
+                  if (!(a.dbg & 4)) tc_mma2(d_tmem, alo, whi, kIdescBf16, 1);
+                  if (!(a.dbg & 1)) tc_mma2(d_tmem, ahi, wlo, kIdescBf16, 1);
+                }
               }
-              tc_commit2(bWEmpty + 8 * stage);  // frees the stage in both CTAs when these MMAs have read it
-              if (++stage == NS) { stage = 0; phase ^= 1; }
+              if (el) tc_commit2(bWEmpty + 8 * stage);  // frees the stage in both CTAs when these MMAs have read it
+              __syncwarp();
+              if (++stage == ns_eff) { stage = 0; phase ^= 1; }
             }
-            tc_commit2(bDFull + 8 * (t * 2 + (step & 1)));  // accumulator of (tile t, step) complete, both CTAs
+            if (elect_one()) tc_commit2(bDFull + 8 * (t * 2 + (step & 1)));  // accumulator of (tile t, step) complete, both CTAs
+            __syncwarp();
           }
         }
       }
+      if (prof && lane == 0) { a.prof[0] = clock64() - t_begin; a.prof[1] = tp1; a.prof[2] = tp2; a.prof[3] = 0; }
     }
   } else {
     // ============================================================ epilogue
@@ -355,6 +394,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     e.a_ready = mapa_rank(bAReady, 0);
     e.d_full = bDFull;
     e.abort_flag = abort_flag;
+    e.prof = prof;
     const int w8 = e.qh * 4 + e.sub;  // index among the 8 warps that share this thread's row
     uint32_t d_par = 0;               // bit t*2+b = parity to wait for on d_full[t][b]
     for (int su = cluster_id; su < n_super; su += n_clusters) {
@@ -369,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
         float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(e.qh * 32 + e.sub * 8 + i, 0, px, py, pz, a.embed_w);
-        t2_store_a(e, t, e.qh * 32 + e.sub * 8, x);
+        t2_store_a(e, t, e.qh * 32 + e.sub * 8, 0, x);
       }
       float ha0 = 0.f, ha1 = 0.f, ha2 = 0.f, ha3 = 0.f, hb0 = 0.f, hb1 = 0.f, hb2 = 0.f, hb3 = 0.f;
       bool ok = true;
@@ -377,7 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
   for (int t = 0; t < 2 && ok; ++t) {                                                                                              \
     float h0 = t ? hb0 : ha0, h1 = t ? hb1 : ha1, h2 = t ? hb2 : ha2, h3 = t ? hb3 : ha3;                                          \
     ok = t2_epi<MODE, KIND>(a, e, t, STEP, L, STORE, t ? x1 : x0, t ? y1 : y0, t ? z1 : z0, t ? v1 : v0, t ? p1 : p0, h0, h1, h2, \
-                            h3, d_par);                                                                                            \
+                            h3, d_par, tp0);                                                                                       \
     if (t) { hb0 = h0, hb1 = h1, hb2 = h2, hb3 = h3; } else { ha0 = h0, ha1 = h1, ha2 = h2, ha3 = h3; }                            \
   }
       for (int l = 0; l < 8 && ok; ++l) { T2_STEP(0, l, l, (MODE == MLP_SDF_REV) || l < 7) }
@@ -419,6 +459,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
       }
       epi_bar();  // the scratch is overwritten by the next super-tile's prologue
     }
+    if (prof && lane == 0 && (warp == 2 || warp == 17)) {
+      const int o = 16 + 8 * (int)rank + (warp == 17 ? 4 : 0);
+      a.prof[o] = clock64() - t_begin;
+      a.prof[o + 1] = tp0;
+    }
   }
 tc2_done:
   tc_fence_before();
@@ -444,8 +489,8 @@ static inline int tc2_grid(hold_ctx* ctx, int P) {
 
 // HOLD_TC_PAIR=1 selects the pair kernels (off by default until validated on hardware).
 static inline bool tc2_enabled() {
-  static const bool on = [] { const char* e = getenv("HOLD_TC_PAIR"); return e != nullptr && atoi(e) != 0; }();
-  return on;
+  const char* e = getenv("HOLD_TC_PAIR");
+  return e != nullptr && atoi(e) != 0;
 }
 
 // SDF net on P canonical points: sdf only (sampler rounds), or sdf + gradient + feature (reverse mode).
@@ -465,6 +510,13 @@ static int tc2_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, 
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
+  { const char* e = getenv("HOLD_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
+  if (getenv("HOLD_TC_PROF") != nullptr) {
+    void* pr = nullptr;
+    int rc = ws_get(ctx, 23 /* WS_PROF (debug) */, 64 * sizeof(long long), &pr);
+    if (rc) return rc;
+    a.prof = (long long*)pr;
+  }
   const int grid = tc2_grid(ctx, P);
   if (rev) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
