@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 8);
           uint32_t raw[8];
           tc_ld8(t_col, raw);
+#pragma unroll 2
           for (int h = 0; h < 8; ++h) {
             const int n0 = h * 32 + sub * 8;
             const float bv[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
@@ -570,6 +571,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
         uint32_t raw[8];
         tc_ld8(t_col, raw);
+#pragma unroll 2
         for (int h = 0; h < 8; ++h) {
           const int n0 = h * 32 + sub * 8;
           // bias of this hand-off was requested one hand-off earlier (L1 is ~0 KB at this smem carve-out: an
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               o = z;
             } else {
               float e = 0.f;
-              const float sp = (a.dbg & 2) ? fmaxf(z, 0.f) * kTcScaleA : softplus100_fast(z, e);
+              const float sp = softplus100_fast(z, e);
               if (MODE == MLP_SDF_JVP) {
                 // softplus'(z) of the VALUE row (lane & ~3), applied to the tangent rows
                 const float r = mufu_rcp(1.0f + e) * kTcScaleA;   // e = exp(-|100 z|)
