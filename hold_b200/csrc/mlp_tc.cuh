@@ -1,9 +1,10 @@
 // tcgen05 (5th-gen tensor core) fused MLP chains — HOLD_MLP_TC.
 //
 // One persistent CTA per SM walks 128-row tiles through the whole layer chain:
-//   * warp 0 (1 lane)  : bulk-async (TMA engine) copies of pre-swizzled fp16 weight chunks L2 -> smem ring
-//   * warp 1 (1 lane)  : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
-//   * warps 2..5       : epilogue — tcgen05.ld the accumulator in 64-column chunks, bias + activation in fp32,
+//   * warp 0           : bulk-async (TMA engine) copies of pre-swizzled fp16 weight chunks L2 -> smem ring
+//   * warp 1           : tcgen05.mma issuer; D[128 x 256] fp32 accumulators in TMEM, ping-pong per layer
+//                        (both walk their loops warp-uniformly and elect the issuing lane, see elect_one())
+//   * warps 2..17      : epilogue — tcgen05.ld the accumulator in 32-column hand-offs, bias + activation in fp32,
 //                        split into fp16 hi/lo and write the next layer's A operand (SW128 K-major) to smem;
 //                        chunk-level mbarriers let layer l+1's MMAs start while layer l's epilogue is running.
 // Arithmetic: every fp32 operand x is split x = hi + lo (fp16 each: 11 + 11 mantissa bits) and each product is
@@ -12,7 +13,8 @@
 // 1e-4 parity bar needs: an sdf error eps reaches the density as eps/beta^2 (beta down to 1e-2), so plain bf16
 // (2^-9) and even a bf16 split (2^-16, measured 83 % of pixels within 1e-4) do not meet it (SURVEY §7 "hard
 // parts").  Range: |x| must stay below 65504 (activations/weights here are O(1e-3..1e2)).  The sdf / rgb heads (1 resp. 3 output
-// rows) are fp32 dot products in the epilogue.  Gradients: forward mode, 4 rows per point (see mlp_simt.cuh).
+// rows) are fp32 dot products in the epilogue.  Gradients: reverse mode in the same kernel (MODE 3, default); forward
+// mode with 4 rows per point (MODE 1, HOLD_TC_GRAD=jvp) is kept for A/B.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -22,8 +24,8 @@
 namespace hold {
 
 constexpr int kTcRows = 128;
-constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] bf16 hi (16 KB) + lo (16 KB)
-constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] bf16
+constexpr int kTcStageBytes = 32768;      // one weight stage: [256 n x 32 k] fp16 hi (16 KB) + lo (16 KB)
+constexpr int kTcAChunkBytes = 16384;     // one A chunk: [128 rows x 64 k] fp16
 constexpr int kTcThreads = 192;
 // Power-of-two operand scaling (exact): fp16 operands are fed to the tensor core as A * 2^6 and W * 2^10 so that
 // the LOW halves of the hi/lo split stay in fp16's normal range for |a| >= 2e-3, |w| >= 1.2e-4 (unscaled, the low
@@ -160,7 +162,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 }
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 // kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=128
-constexpr uint32_t kIdescBf16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 // x = hi + lo: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
@@ -335,9 +337,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
               const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
               if (el) {
-                tc_mma(d_tmem, ahi, whi, kIdescBf16, (s | j) != 0);
-                if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescBf16, 1);
-                if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescBf16, 1);
+                tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
+                if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescF16, 1);
+                if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
               }
             }
             if (el) tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
@@ -687,7 +689,7 @@ tc_done:
 }
 
 // ------------------------------------------------------------------------------------------------ packing
-// One stage image = [256 n x 32 k] bf16 in the SW64 K-major canonical layout, hi part then lo part.
+// One stage image = [256 n x 32 k] fp16 in the SW64 K-major canonical layout, hi part then lo part.
 // W[n][k] = scale * fold(v, g)[row_off + n][colmap(k)];  colmap: k -> source column (or -1 => 0).
 __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N, int K,
                           int kpad, float scale, int perm_feat_first, uint8_t* __restrict__ img) {

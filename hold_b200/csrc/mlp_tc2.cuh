@@ -367,9 +367,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
                 const uint64_t whi = umma_desc(wb + jj * 32, 512, kLayoutSW64);
                 const uint64_t wlo = umma_desc(wb + 8192 + jj * 32, 512, kLayoutSW64);
                 if (el) {
-                  tc_mma2(d_tmem, ahi, whi, kIdescBf16, (si | jj) != 0);
-                  if (!(a.dbg & 4)) tc_mma2(d_tmem, alo, whi, kIdescBf16, 1);
-                  if (!(a.dbg & 1)) tc_mma2(d_tmem, ahi, wlo, kIdescBf16, 1);
+                  tc_mma2(d_tmem, ahi, whi, kIdescF16, (si | jj) != 0);
+                  if (!(a.dbg & 4)) tc_mma2(d_tmem, alo, whi, kIdescF16, 1);
+                  if (!(a.dbg & 1)) tc_mma2(d_tmem, ahi, wlo, kIdescF16, 1);
                 }
               }
               if (el) tc_commit2(bWEmpty + 8 * stage);  // frees the stage in both CTAs when these MMAs have read it
