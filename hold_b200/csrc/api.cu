@@ -12,6 +12,7 @@
 #include "mlp_tc2.cuh"
 #include "composite.cuh"
 #include "background.cuh"
+#include "pose_bwd.cuh"
 
 namespace hold {
 
@@ -387,6 +388,51 @@ int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* b
     attr_set = true;
   }
   k_mano_lbs<<<B, 256, smem, (cudaStream_t)stream>>>(d, betas, full_pose, transl, scene_scale, tfs_c_inv, verts, jnts, tfs, v_posed);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_mano_lbs_bwd(hold_ctx* ctx, const hold_mano_model* m, int B, const float* betas, const float* full_pose,
+                      const float* transl, const float* scene_scale, const float* tfs_c_inv, const float* g_verts,
+                      const float* g_jnts, const float* g_tfs, float* g_betas, float* g_pose, float* g_transl, float* g_scale,
+                      void* stream) {
+  HOLD_REQUIRE(ctx && m, "NULL argument");
+  HOLD_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return HOLD_OK;
+  HOLD_REQUIRE(betas && full_pose && transl && scene_scale && g_betas && g_pose && g_transl && g_scale, "NULL tensor");
+  HOLD_REQUIRE(m->parents_host && m->tip_ids_host, "NULL host arrays in mano model");
+  posebwd::ManoPtrs d;
+  d.v_template = m->v_template, d.shapedirs = m->shapedirs, d.posedirs = m->posedirs, d.J_regressor = m->J_regressor;
+  d.lbs_weights = m->lbs_weights, d.hands_mean = m->hands_mean;
+  for (int i = 0; i < kJoints; ++i) {
+    d.parents[i] = (i == 0) ? 0 : m->parents_host[i];
+    HOLD_REQUIRE(i == 0 || (d.parents[i] >= 0 && d.parents[i] < i), "parents must be topologically ordered");
+  }
+  for (int i = 0; i < 5; ++i) {
+    d.tips[i] = m->tip_ids_host[i];
+    HOLD_REQUIRE(d.tips[i] >= 0 && d.tips[i] < kVerts, "tip id out of range");
+  }
+  const int nt = 256, smem = posebwd::mano_scratch_floats(nt) * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HOLD_CUDA(cudaFuncSetAttribute(k_mano_lbs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_mano_lbs_bwd<<<B, nt, smem, (cudaStream_t)stream>>>(d, betas, full_pose, transl, scene_scale, tfs_c_inv, g_verts, g_jnts, g_tfs,
+                                                        g_betas, g_pose, g_transl, g_scale);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_object_tf_bwd(hold_ctx* ctx, int B, const float* rot, const float* trans, const float* scene_scale, float obj_scale,
+                       const float* denorm_mat, const float* pts_cano, int Nv, const float* g_verts, const float* g_tfs,
+                       float* g_rot, float* g_trans, float* g_scene_scale, float* g_obj_scale, void* stream) {
+  HOLD_REQUIRE(ctx && rot && trans && scene_scale && denorm_mat && g_rot && g_trans && g_scene_scale && g_obj_scale, "NULL argument");
+  if (B <= 0) return HOLD_OK;
+  HOLD_REQUIRE(g_verts == nullptr || (pts_cano != nullptr && Nv > 0), "g_verts given without canonical points");
+  const int nt = 256, smem = posebwd::obj_scratch_floats(nt) * (int)sizeof(float);
+  k_object_tf_bwd<<<B, nt, smem, (cudaStream_t)stream>>>(Nv, rot, trans, scene_scale, obj_scale, denorm_mat, pts_cano, g_verts, g_tfs,
+                                                         g_rot, g_trans, g_scene_scale, g_obj_scale);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

@@ -79,6 +79,62 @@ class RenderingNet(nn.Module):
         self.lin_pose = nn.Linear(45 if kind == "hand" else 0, 8)
 
 
+class _ManoLbsFn(torch.autograd.Function):
+    """GenericServer.forward under autograd (fitting/model.py:117): forward = hold_mano_lbs, backward = hold_mano_lbs_bwd."""
+
+    @staticmethod
+    def forward(fctx, server, absolute, scene_scale, transl, thetas, betas):
+        out = server._forward_nograd(scene_scale, transl, thetas, betas, absolute)
+        fctx.server, fctx.absolute = server, absolute
+        fctx.save_for_backward(scene_scale.detach(), transl.detach(), thetas.detach(), betas.detach())
+        fctx.mark_non_differentiable(out["v_posed"])
+        return out["verts"], out["jnts"], out["tfs"], out["v_posed"]
+
+    @staticmethod
+    def backward(fctx, g_verts, g_jnts, g_tfs, _g_vposed):
+        srv = fctx.server
+        scene_scale, transl, thetas, betas = fctx.saved_tensors
+        B = thetas.shape[0]
+        dev = thetas.device
+        f = lambda t, shape: t.detach().float().reshape(shape).contiguous()
+        scene_scale, transl, thetas, betas = f(scene_scale, (B,)), f(transl, (B, 3)), f(thetas, (B, 48)), f(betas.expand(B, 10), (B, 10))
+        gc = lambda g: None if g is None else g.float().contiguous()
+        g_verts, g_jnts, g_tfs = gc(g_verts), gc(g_jnts), gc(g_tfs)
+        gb, gp, gt, gs = (torch.empty(B, 10, device=dev), torch.empty(B, 48, device=dev), torch.empty(B, 3, device=dev),
+                          torch.empty(B, device=dev))
+        m = srv._model()
+        tci = None if (fctx.absolute or srv.tfs_c_inv is None) else srv.tfs_c_inv
+        check(lib().hold_mano_lbs_bwd(srv.ctx.h, C.byref(m), B, ptr(betas), ptr(thetas), ptr(transl), ptr(scene_scale), ptr(tci),
+                                      ptr(g_verts), ptr(g_jnts), ptr(g_tfs), ptr(gb), ptr(gp), ptr(gt), ptr(gs), stream_ptr()))
+        return None, None, gs, gt, gp, gb
+
+
+class _ObjectTfFn(torch.autograd.Function):
+    """ObjectModel.forward under autograd: forward = hold_object_tf, backward = hold_object_tf_bwd."""
+
+    @staticmethod
+    def forward(fctx, server, scene_scale, transl, thetas, obj_scale):
+        out = server._forward_nograd(scene_scale, transl, thetas, float(obj_scale))
+        fctx.server = server
+        fctx.save_for_backward(scene_scale.detach(), transl.detach(), thetas.detach(), obj_scale.detach())
+        return out["verts"], out["obj_tfs"]
+
+    @staticmethod
+    def backward(fctx, g_verts, g_tfs):
+        srv = fctx.server
+        scene_scale, transl, thetas, obj_scale = fctx.saved_tensors
+        B = thetas.shape[0]
+        dev = srv.v3d_cano.device
+        f = lambda t, shape: t.detach().float().reshape(shape).contiguous()
+        gc = lambda g, shape: None if g is None else g.float().reshape(shape).contiguous()
+        Nv = srv.v3d_cano.shape[0]
+        gr, gt, gs, go = torch.empty(B, 3, device=dev), torch.empty(B, 3, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev)
+        check(lib().hold_object_tf_bwd(srv.ctx.h, B, ptr(f(thetas, (B, 3))), ptr(f(transl, (B, 3))), ptr(f(scene_scale, (B,))),
+                                       float(obj_scale), ptr(srv.denorm_mat), ptr(srv.v3d_cano), Nv, ptr(gc(g_verts, (B, Nv, 3))),
+                                       ptr(gc(g_tfs, (B, 4, 4))), ptr(gr), ptr(gt), ptr(gs), ptr(go), stream_ptr()))
+        return None, gs.reshape(scene_scale.shape), gt.reshape(transl.shape), gr.reshape(thetas.shape), go.sum().reshape(obj_scale.shape)
+
+
 class MANOServer(nn.Module):
     """model/mano/server.py:20-133 (GenericServer + MANOServer) over a MANO model struct
     (dict with v_template, shapedirs, posedirs, J_regressor, lbs_weights, hands_mean, parents, tip_ids)."""
@@ -109,6 +165,17 @@ class MANOServer(nn.Module):
         return m
 
     def forward(self, scene_scale, transl, thetas, betas, absolute=False):
+        """Differentiable w.r.t. scene_scale / transl / thetas / betas when any of them requires grad (the pose refinement
+        of optimize_ckpt.py); otherwise the plain forward."""
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (scene_scale, transl, thetas, betas)):
+            B = thetas.shape[0]
+            verts, jnts, tfs, v_posed = _ManoLbsFn.apply(self, absolute, scene_scale.reshape(B), transl.reshape(B, 3),
+                                                         thetas.reshape(B, 48), betas.expand(B, 10))
+            return {"verts": verts, "jnts": jnts, "tfs": tfs, "v_posed": v_posed,
+                    "skin_weights": self.m["lbs_weights"][None].expand(B, -1, -1)}
+        return self._forward_nograd(scene_scale, transl, thetas, betas, absolute)
+
+    def _forward_nograd(self, scene_scale, transl, thetas, betas, absolute=False):
         B = thetas.shape[0]
         dev = thetas.device
         f = lambda t, shape: t.detach().float().reshape(shape).contiguous()
@@ -146,13 +213,24 @@ class ObjectServer(nn.Module):
         self.verts_c = self.v3d_cano[None]
 
     def forward(self, scene_scale, transl, thetas, absolute=False):
+        """Differentiable w.r.t. scene_scale / transl / thetas / obj_scale (when `self.obj_scale` is a tensor, as
+        fitting/model.py:113 sets it) if any of them requires grad; otherwise the plain forward."""
+        osc = self.obj_scale
+        needs = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (scene_scale, transl, thetas, osc))
+        if needs:
+            osc_t = osc if torch.is_tensor(osc) else torch.tensor(float(osc), device=self.v3d_cano.device)
+            verts, tfs = _ObjectTfFn.apply(self, scene_scale, transl, thetas, osc_t)
+            return {"verts": verts, "obj_tfs": tfs}
+        return self._forward_nograd(scene_scale, transl, thetas, float(osc))
+
+    def _forward_nograd(self, scene_scale, transl, thetas, obj_scale):
         B = thetas.shape[0]
         dev = self.v3d_cano.device
         f = lambda t, shape: t.detach().float().reshape(shape).contiguous()
         tfs = torch.empty(B, 4, 4, device=dev)
         verts = torch.empty(B, self.v3d_cano.shape[0], 3, device=dev)
         check(lib().hold_object_tf(self.ctx.h, B, ptr(f(thetas, (B, 3))), ptr(f(transl, (B, 3))), ptr(f(scene_scale, (B,))),
-                                   self.obj_scale, ptr(self.denorm_mat), ptr(self.v3d_cano), self.v3d_cano.shape[0],
+                                   float(obj_scale), ptr(self.denorm_mat), ptr(self.v3d_cano), self.v3d_cano.shape[0],
                                    ptr(tfs), ptr(verts), stream_ptr()))
         return {"verts": verts, "obj_tfs": tfs[:, None]}
 

@@ -148,6 +148,19 @@ int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* b
                   const float* full_pose /*[B,48]*/, const float* transl /*[B,3]*/, const float* scene_scale /*[B]*/,
                   const float* tfs_c_inv /*[16,4,4] or NULL*/, float* verts, float* jnts, float* tfs, float* v_posed,
                   void* stream);
+/* Reverse mode of hold_mano_lbs — what torch.autograd computes through GenericServer.forward for the pose refinement
+ * of optimize_ckpt.py (fitting/model.py:117).  Upstream gradients g_verts [B,778,3], g_jnts [B,21,3],
+ * g_tfs [B,16,4,4] (each may be NULL = zero) -> g_betas [B,10], g_pose [B,48], g_transl [B,3], g_scale [B].
+ * Deterministic (fixed-order sums). */
+int hold_mano_lbs_bwd(hold_ctx* ctx, const hold_mano_model* m, int B, const float* betas, const float* full_pose,
+                      const float* transl, const float* scene_scale, const float* tfs_c_inv, const float* g_verts,
+                      const float* g_jnts, const float* g_tfs, float* g_betas, float* g_pose, float* g_transl, float* g_scale,
+                      void* stream);
+/* Reverse mode of hold_object_tf (ObjectModel.forward under autograd).  g_verts [B,Nv,3], g_tfs [B,4,4] (nullable) ->
+ * g_rot [B,3], g_trans [B,3], g_scene_scale [B], g_obj_scale [B] (per-frame terms of the scalar's gradient). */
+int hold_object_tf_bwd(hold_ctx* ctx, int B, const float* rot, const float* trans, const float* scene_scale, float obj_scale,
+                       const float* denorm_mat, const float* pts_cano, int Nv, const float* g_verts, const float* g_tfs,
+                       float* g_rot, float* g_trans, float* g_scene_scale, float* g_obj_scale, void* stream);
 /* a17: ObjectModel.forward (model/obj/object_model.py:29-70). */
 int hold_object_tf(hold_ctx* ctx, int B, const float* rot /*[B,3]*/, const float* trans /*[B,3]*/,
                    const float* scene_scale /*[B]*/, float obj_scale, const float* denorm_mat /*[4,4]*/,

@@ -310,23 +310,23 @@ def rodrigues(rv):
     rx, ry, rz = d[:, 0:1], d[:, 1:2], d[:, 2:3]
     z = torch.zeros_like(rx)
     Km = torch.cat([z, -rz, ry, rz, z, -rx, -ry, rx, z], 1).view(-1, 3, 3)
-    return torch.eye(3)[None] + s * Km + (1 - c) * torch.bmm(Km, Km)
+    return torch.eye(3, dtype=rv.dtype)[None] + s * Km + (1 - c) * torch.bmm(Km, Km)
 
 
 def mano_lbs(m, betas, full_pose):
     """`lbs()` utils/external/lbs.py:139-251 as driven by MANO.forward (body_models.py:601-685,
     flat_hand_mean=False so pose += [0,0,0,hands_mean]).  Returns verts, joints(16), A, v_posed."""
     B = full_pose.shape[0]
-    pose = full_pose + torch.cat([torch.zeros(3), m["hands_mean"]])[None]
+    pose = full_pose + torch.cat([torch.zeros(3, dtype=full_pose.dtype), m["hands_mean"]])[None]
     v_shaped = m["v_template"][None] + torch.einsum("bl,mkl->bmk", betas, m["shapedirs"])
     J = torch.einsum("bik,ji->bjk", v_shaped, m["J_regressor"])
     Rm = rodrigues(pose.reshape(-1, 3)).view(B, 16, 3, 3)
-    pf = (Rm[:, 1:] - torch.eye(3)).reshape(B, -1)
+    pf = (Rm[:, 1:] - torch.eye(3, dtype=Rm.dtype)).reshape(B, -1)
     v_posed = v_shaped + torch.matmul(pf, m["posedirs"]).view(B, -1, 3)
     par = m["parents"]
     rel = J.clone()
     rel[:, 1:] = rel[:, 1:] - J[:, par[1:]]
-    Tm = torch.zeros(B, 16, 4, 4)
+    Tm = torch.zeros(B, 16, 4, 4, dtype=full_pose.dtype)
     Tm[:, :, :3, :3] = Rm
     Tm[:, :, :3, 3] = rel
     Tm[:, :, 3, 3] = 1.0
@@ -350,9 +350,8 @@ def mano_server(m, scene_scale, transl, full_pose, betas, tfs_c_inv=None):
     s = scene_scale.view(-1, 1, 1)
     t = transl.view(-1, 1, 3)
     out = {"verts": verts * s + t * s, "jnts": joints * s + t * s}
-    tf = A.clone()
-    tf[:, :, :3, :] = tf[:, :, :3, :] * s.view(-1, 1, 1, 1)
-    tf[:, :, :3, 3] = tf[:, :, :3, 3] + t * s
+    top = A[:, :, :3, :] * s.view(-1, 1, 1, 1)                        # server.py:90-93, written without in-place
+    tf = torch.cat([torch.cat([top[..., :3], (top[..., 3] + t * s)[..., None]], -1), A[:, :, 3:4, :]], 2)   # ops: differentiable
     if tfs_c_inv is not None:
         tf = torch.einsum("bnij,njk->bnik", tf, tfs_c_inv)
     out["tfs"] = tf
@@ -387,12 +386,13 @@ def axis_angle_to_matrix(aa):
 def object_server(rot, trans, scene_scale, obj_scale, denorm_mat, pts_cano):
     """ObjectModel.forward, model/obj/object_model.py:29-70 -> (obj_tfs [B,4,4], verts [B,Nv,3])."""
     B = rot.shape[0]
-    tf = torch.eye(4).repeat(B, 1, 1)
+    eye = torch.eye(4, dtype=rot.dtype)
+    tf = eye.repeat(B, 1, 1)
     tf[:, :3, :3] = axis_angle_to_matrix(rot)
     tf[:, :3, 3] = trans
-    sm = torch.eye(4).repeat(B, 1, 1) * scene_scale[:, None, None]
+    sm = eye.repeat(B, 1, 1) * scene_scale[:, None, None]
     sm[:, 3, 3] = 1
-    om = torch.eye(4).repeat(B, 1, 1) * obj_scale
+    om = eye.repeat(B, 1, 1) * obj_scale
     om[:, 3, 3] = 1
     tf = torch.matmul(torch.matmul(torch.matmul(sm, tf), om), denorm_mat[None].repeat(B, 1, 1))
     vh = F.pad(pts_cano, (0, 1), value=1.0)[None].repeat(B, 1, 1)

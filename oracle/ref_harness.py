@@ -286,7 +286,53 @@ def check():
         for key in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
             ok &= _cmp(f"comp.{key}", oo[0]["render"]["comp"][key], ro[0]["render"]["comp"][key], 1e-4)
     ok &= check_background()
+    ok &= check_pose_grads()
     print("ORACLE == REFERENCE" if ok else "ORACLE != REFERENCE")
+    return ok
+
+
+def check_pose_grads():
+    """Gradients of the pose servers: torch.autograd through the REFERENCE's lbs() / ObjectModel.forward against
+    torch.autograd through the oracle's restatement (the oracle for hold_mano_lbs_bwd / hold_object_tf_bwd)."""
+    from hold_b200 import synth
+    from oracle import hold_oracle as O
+    from src.model.obj.object_model import ObjectModel
+    from src.utils.external.lbs import lbs
+
+    sc = synth.make_scene(H=4, W=4, S=32, nodes=("right", "object"), B=2, seed=11)
+    m = sc.mano["right"]
+    p = sc.params["right"]
+    g = torch.Generator().manual_seed(1)
+    gv, gj = torch.randn(2, 778, 3, generator=g), torch.randn(2, 16, 3, generator=g)
+    pose_mean = torch.cat([torch.zeros(3), m["hands_mean"]])
+    leaves = lambda: [t.clone().requires_grad_() for t in (sc.betas["right"][None].repeat(2, 1), torch.cat([p["global_orient"], p["pose"]], 1), p["transl"])]
+    be, th, tr = leaves()
+    verts, joints, *_ = lbs(be, th + pose_mean, m["v_template"], m["shapedirs"], m["posedirs"], m["J_regressor"], m["parents"], m["lbs_weights"])
+    s = float(sc.scene_scale)
+    ref = torch.autograd.grad((((verts + tr[:, None]) * s) * gv).sum() + (((joints + tr[:, None]) * s) * gj).sum(), (be, th, tr))
+    be, th, tr = leaves()
+    out = O.mano_server(m, torch.full((2,), s), tr, th, be)
+    got = torch.autograd.grad((out["verts"] * gv).sum() + (out["jnts"][:, :16] * gj).sum(), (be, th, tr))
+    print("[pose-server gradients]")
+    ok = True
+    for name, a, b in zip(("hand.g_betas", "hand.g_pose", "hand.g_transl"), got, ref):
+        ok &= _cmp(name, a, b, 1e-5)
+    po = sc.params["object"]
+    om = ObjectModel.__new__(ObjectModel)
+    torch.nn.Module.__init__(om)
+    om.register_buffer("obj_scale", torch.FloatTensor([1.0]))
+    om.register_buffer("v3d_cano", sc.obj_pts_cano)
+    om.register_buffer("norm_mat", torch.eye(4))
+    om.register_buffer("denorm_mat", torch.eye(4))
+    gvo = torch.randn(2, sc.obj_pts_cano.shape[0], 3, generator=g)
+    r1, t1, s1 = po["global_orient"].clone().requires_grad_(), po["transl"].clone().requires_grad_(), torch.full((2,), s).requires_grad_()
+    o = om.forward(r1, t1, s1)
+    ref = torch.autograd.grad((o["vertices"] * gvo).sum(), (r1, t1, s1))
+    r2, t2, s2 = po["global_orient"].clone().requires_grad_(), po["transl"].clone().requires_grad_(), torch.full((2,), s).requires_grad_()
+    _, v = O.object_server(r2, t2, s2, 1.0, torch.eye(4), sc.obj_pts_cano)
+    got = torch.autograd.grad((v * gvo).sum(), (r2, t2, s2))
+    for name, a, b in zip(("object.g_rot", "object.g_trans", "object.g_scene_scale"), got, ref):
+        ok &= _cmp(name, a, b, 1e-5)
     return ok
 
 
