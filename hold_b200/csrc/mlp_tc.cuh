@@ -33,6 +33,18 @@ constexpr int kTcThreads = 192;
 // rescaled by 2^-16 in the epilogue's bias FMA.  Range: |a| < 1023, |w| < 64.
 constexpr float kTcScaleA = 64.0f, kTcScaleW = 1024.0f, kTcUnscale = 1.0f / (64.0f * 1024.0f);
 
+// LEAN variant (HOLD_TC_LEAN=1, SDF chains): the epilogue works in the base-2 domain of Softplus(beta=100),
+//   softplus(z) = (ln2/100) * S(t),  t = 100 z log2(e),  S(t) = max(t, 0) + lg2(1 + 2^-|t|),
+// t comes straight out of the accumulator by ONE fma (bias pre-multiplied by 100 log2 e), S is the next layer's A
+// operand as is, and the factor ln2/100 lives in the next layer's weight image (columns fed by activations: W * ln2/100 *
+// 2^17; columns fed by the embedding, A = 64 embed: W * 2^11; accumulator = 2^17 z either way).  6 instead of 8
+// instructions per element, same two MUFU ops.
+constexpr float kLeanAccToT = 144.26950408889634f / 131072.0f;      // accumulator (2^17 z) -> t
+constexpr float kLeanAccToZ = 1.0f / 131072.0f;                      // accumulator -> z (feature layer)
+constexpr float kLeanBiasToT = 144.26950408889634f;                  // bias -> bias_t
+constexpr float kLeanAct = 0.6931471805599453f * 0.01f;              // S -> softplus
+constexpr float kLeanWAct = kLeanAct * 131072.0f, kLeanWEmb = 2048.0f;  // weight image scales per input column type
+
 constexpr int kTcMaxSteps = 17;
 struct TcLayer {
   const uint8_t* wimg;  // pre-swizzled stage images, nst * 32 KB
@@ -41,7 +53,15 @@ struct TcLayer {
   int N;                // valid outputs
 };
 
+__global__ void k_scale_vec(const float* __restrict__ src, int n, float c, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = c * src[i];
+}
+
 struct TcMlp {
+  uint8_t* sdf_imgL[HOLD_MAX_LAYERS] = {nullptr};  // LEAN images of layers 0..8 (per-column operand scales)
+  float* sdf_bias_t[8] = {nullptr};                 // LEAN: bias * 100 log2(e), layers 0..7
+  float* w_last_t = nullptr;                        // LEAN: sdf head row * ln2/100
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient
@@ -198,6 +218,13 @@ __device__ __forceinline__ float softplus100_fast(float z, float& u_out) {
   return fmaf(L, 0.6931471805599453f * 0.01f * kTcScaleA, fmaxf(z, 0.f) * kTcScaleA);
 }
 
+// S(t) of the LEAN variant; u_out = 2^-|t| for the derivative
+__device__ __forceinline__ float softplus_t(float t, float& u_out) {
+  const float u = mufu_ex2(-fabsf(t));
+  u_out = u;
+  return fmaxf(t, 0.f) + mufu_lg2(1.0f + u);
+}
+
 // One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
 // w.r.t. coordinate comp-1.  Deliberately NOT inlined: it is called from rolled loops at the tile prologue and
 // at the skip layer, and inlining 39 sinf/cosf bodies would blow the instruction cache of the hot epilogue.
@@ -252,8 +279,9 @@ struct TcCfg {
   static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
-template <int MODE>
+template <int MODE, bool LEAN = false>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
+  static_assert(!LEAN || MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV, "LEAN: SDF chains only");
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
@@ -457,16 +485,21 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             tc_wait_ld();
             float acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * kTcUnscale;
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * ((LEAN && kind <= 1) ? 1.0f : kTcUnscale);
             if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
             float out[8];
             if (kind == 0) {
               float sg[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float z = acc[i] + bv[i];
-                float e;
-                out[i] = softplus100_fast(z, e);
+                float e, z;
+                if (LEAN) {
+                  z = fmaf(acc[i], kLeanAccToT, bv[i]);   // t (same sign as z)
+                  out[i] = softplus_t(z, e);
+                } else {
+                  z = acc[i] + bv[i];
+                  out[i] = softplus100_fast(z, e);
+                }
                 const float r = mufu_rcp(1.0f + e);
                 sg[i] = (z >= 0.f) ? r : e * r;
               }
@@ -487,15 +520,18 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             } else if (kind == 1) {
               if (valid) {
                 float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
-                dst[0] = make_float4(acc[0] + bv[0], acc[1] + bv[1], acc[2] + bv[2], acc[3] + bv[3]);
-                dst[1] = make_float4(acc[4] + bv[4], acc[5] + bv[5], acc[6] + bv[6], acc[7] + bv[7]);
+                const float fs = LEAN ? kLeanAccToZ : 1.0f;
+                dst[0] = make_float4(fmaf(acc[0], fs, bv[0]), fmaf(acc[1], fs, bv[1]), fmaf(acc[2], fs, bv[2]), fmaf(acc[3], fs, bv[3]));
+                dst[1] = make_float4(fmaf(acc[4], fs, bv[4]), fmaf(acc[5], fs, bv[5]), fmaf(acc[6], fs, bv[6]), fmaf(acc[7], fs, bv[7]));
               }
               const float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0);
               const float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0 + 4);
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
               const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
-              out[0] = kTcScaleA * w0.x * s0.x, out[1] = kTcScaleA * w0.y * s0.y, out[2] = kTcScaleA * w0.z * s0.z, out[3] = kTcScaleA * w0.w * s0.w;
-              out[4] = kTcScaleA * w1.x * s1.x, out[5] = kTcScaleA * w1.y * s1.y, out[6] = kTcScaleA * w1.z * s1.z, out[7] = kTcScaleA * w1.w * s1.w;
+              // g_7 = w_sdf * s_7, times the operand scale (LEAN: a.w_last holds w_sdf * ln2/100)
+              constexpr float ks = LEAN ? (kTcScaleA / kLeanAct) : kTcScaleA;
+              out[0] = ks * w0.x * s0.x, out[1] = ks * w0.y * s0.y, out[2] = ks * w0.z * s0.z, out[3] = ks * w0.w * s0.w;
+              out[4] = ks * w1.x * s1.x, out[5] = ks * w1.y * s1.y, out[6] = ks * w1.z * s1.z, out[7] = ks * w1.w * s1.w;
             } else if (kind == 2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) out[i] = kTcScaleA * acc[i] * bv[i];
@@ -553,7 +589,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             for (int w = 0; w < kTcW; ++w) acc += scratch[(w * 4 + k) * kTcRows + row];
             hsum[k] = acc;
           }
-          a.sdf[p] = hsum[0] * (1.0f / kTcScaleA) + a.b_last[0];
+          a.sdf[p] = hsum[0] * (LEAN ? 1.0f : (1.0f / kTcScaleA)) + a.b_last[0];
           a.grad[3 * (size_t)p] = hsum[1], a.grad[3 * (size_t)p + 1] = hsum[2], a.grad[3 * (size_t)p + 2] = hsum[3];
         }
         epi_bar();
@@ -594,7 +630,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           for (int i = 0; i < 8; ++i) {
             // accumulator -> pre-activation (undo the operand scaling, add the bias on value rows); out[] holds the
             // next layer's operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
-            const float z = fmaf(acc[i], kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
+            const float z = fmaf(acc[i], LEAN ? kLeanAccToT : kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
             float o;
             if (MODE == MLP_COLOR) {
               o = fmaxf(z, 0.f) * kTcScaleA;
@@ -602,7 +638,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               o = z;
             } else {
               float e = 0.f;
-              const float sp = softplus100_fast(z, e);
+              const float sp = LEAN ? softplus_t(z, e) : softplus100_fast(z, e);
               if (MODE == MLP_SDF_JVP) {
                 // softplus'(z) of the VALUE row (lane & ~3), applied to the tangent rows
                 const float r = mufu_rcp(1.0f + e) * kTcScaleA;   // e = exp(-|100 z|)
@@ -666,7 +702,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           float acc = 0.f;
 #pragma unroll
           for (int w = 0; w < kTcW; ++w) acc += scratch[(w * NH + k) * kTcRows + row];
-          h[k] = acc * (1.0f / kTcScaleA);  // the head saw activations times kTcScaleA
+          h[k] = acc * (LEAN ? 1.0f : (1.0f / kTcScaleA));  // the head saw activations times kTcScaleA (LEAN: S, with pre-scaled head weights)
         }
         if (MODE == MLP_COLOR) {
 #pragma unroll
@@ -691,8 +727,10 @@ tc_done:
 // ------------------------------------------------------------------------------------------------ packing
 // One stage image = [256 n x 32 k] fp16 in the SW64 K-major canonical layout, hi part then lo part.
 // W[n][k] = scale * fold(v, g)[row_off + n][colmap(k)];  colmap: k -> source column (or -1 => 0).
+// Operand scale per input column: cs_lo for k < split, cs_hi for k >= split (plain images: kTcScaleW everywhere).
 __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N, int K,
-                          int kpad, float scale, int perm_feat_first, uint8_t* __restrict__ img) {
+                          int kpad, float scale, int perm_feat_first, float cs_lo, float cs_hi, int split,
+                          uint8_t* __restrict__ img) {
   const int n = blockIdx.x;  // 0..255
   __shared__ float red[32];
   __shared__ float f_sh;
@@ -722,7 +760,7 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
       else if (k < kFeat + 14) src = k - kFeat;
       else src = k;
     }
-    float w = (n < N && src < K) ? kTcScaleW * (scale * (vr[src] * f)) : 0.f;
+    float w = (n < N && src < K) ? ((k < split) ? cs_lo : cs_hi) * (scale * (vr[src] * f)) : 0.f;
     __half h = __float2half_rn(w);
     __half l = __float2half_rn(w - __half2float(h));
     const int st = k >> 5, kk = k & 31;
@@ -763,6 +801,8 @@ static int tc_init(hold_ctx*) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_JVP>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
   return HOLD_OK;
 }
@@ -773,7 +813,10 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->sdf_img[l]) cudaFree(ns.tc->sdf_img[l]);
     if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
     if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
+    if (ns.tc->sdf_imgL[l]) cudaFree(ns.tc->sdf_imgL[l]);
+    if (l < 8 && ns.tc->sdf_bias_t[l]) cudaFree(ns.tc->sdf_bias_t[l]);
   }
+  if (ns.tc->w_last_t) cudaFree(ns.tc->w_last_t);
   delete ns.tc;
   ns.tc = nullptr;
 }
@@ -788,8 +831,20 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     t.sdf_nst[l] = kpad / 32;
     if (!t.sdf_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_img[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
-    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
+    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, kTcScaleW, kTcScaleW, 0,
+                                  t.sdf_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
+    // LEAN image: layer 0 is fed by the embedding, layer 4 by activations (k < 217) and the embedding (skip), the rest by activations
+    if (!t.sdf_imgL[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgL[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
+    const int split = (l == 0) ? 0 : ((l == 4) ? kHidden - kEmbed : kpad);
+    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, kLeanWAct, kLeanWEmb, split,
+                                  t.sdf_imgL[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+    if (l < 8) {
+      if (!t.sdf_bias_t[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_bias_t[l], 256 * sizeof(float)));
+      k_scale_vec<<<1, 256, 0, s>>>(ns.sdf.bias[l], 256, kLeanBiasToT, t.sdf_bias_t[l]);
+      HOLD_LAUNCH_CHECK(ctx);
+    }
   }
   for (int l = 0; l < 8; ++l) {  // W_l^T for the reverse-mode gradient (layers 7..0)
     const int K_in = (l == 0) ? kEmbed : kHidden, N_out = (l == 3) ? kHidden - kEmbed : kHidden;
@@ -802,9 +857,13 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     const int K = (l == 0) ? rgb->in_dim[0] : 256, kpad = (l == 0) ? 320 : 256;
     t.rgb_nst[l] = kpad / 32;
     if (!t.rgb_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img[l], (size_t)t.rgb_nst[l] * kTcStageBytes));
-    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 1 : 0, t.rgb_img[l]);
+    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 1 : 0, kTcScaleW, kTcScaleW, 0,
+                                  t.rgb_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
+  if (!t.w_last_t) HOLD_CUDA(cudaMalloc((void**)&t.w_last_t, 256 * sizeof(float)));
+  k_scale_vec<<<1, 256, 0, s>>>(ns.sdf.w_last, 256, kLeanAct, t.w_last_t);
+  HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }
 
@@ -821,6 +880,12 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
   { const char* e = getenv("HOLD_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
   static const bool use_jvp = [] { const char* e = getenv("HOLD_TC_GRAD"); return e != nullptr && strcmp(e, "jvp") == 0; }();
+  const bool lean = [] { const char* e = getenv("HOLD_TC_LEAN"); return e != nullptr && atoi(e) != 0; }() && !(jvp && use_jvp);
+  if (lean) {  // base-2-domain epilogue: own weight images, pre-scaled biases and head row
+    for (int l = 0; l < 9; ++l) a.L[l].wimg = ns.tc->sdf_imgL[l];
+    for (int l = 0; l < 8; ++l) a.L[l].bias = ns.tc->sdf_bias_t[l];
+    a.w_last = ns.tc->w_last_t;
+  }
   if (jvp && !use_jvp) {
     // reverse mode: 8 forward layers, feature layer, 8 backward layers over the transposed images
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
@@ -833,14 +898,16 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
     for (int i = 0; i < 8; ++i) {
       a.L[9 + i].wimg = ns.tc->sdf_imgT[7 - i], a.L[9 + i].bias = nullptr, a.L[9 + i].nst = 8, a.L[9 + i].N = 256;
     }
-    k_mlp_tc<MLP_SDF_REV><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
+    if (lean) k_mlp_tc<MLP_SDF_REV, true><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
+    else k_mlp_tc<MLP_SDF_REV><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
   } else if (jvp) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     int tiles = ceil_div(P, kTcRows / 4);
     k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
   } else {
     int tiles = ceil_div(P, kTcRows);
-    k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    if (lean) k_mlp_tc<MLP_SDF_ONLY, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    else k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;

@@ -108,16 +108,19 @@ struct T2Epi {            // per-thread constants of an epilogue warp
   uint32_t d_full;        // local d_full[2][2]
   volatile int* abort_flag;
   int row, qh, sub, lane; // row 0..63 inside the CTA's half tile; qh = column half; sub = warp of the quarter
-  bool prof;
+  bool prof, coarse;
 };
 
-__device__ __forceinline__ void t2_store_a(const T2Epi& e, int t, int n0, int round, const float (&out)[8]) {
+// `arrive`: fine-grained mode arrives after every round on a_ready[t][round]; coarse mode (HOLD_TC_DBG & 32) only after a
+// warp's last round of the tile-step, on a_ready[t][0] — one fence + one remote arrival per warp and tile-step.
+__device__ __forceinline__ void t2_store_a(const T2Epi& e, int t, int n0, int round, bool arrive, const float (&out)[8]) {
   uint4 hi, lo;
   split8(out, hi, lo);
   const int c64 = n0 >> 6, ju = (n0 & 63) >> 3;
   const uint32_t off = (uint32_t)(t * kT2ATile + c64 * 8192 + (e.row >> 3) * 1024 + (e.row & 7) * 128 + ((ju ^ (e.row & 7)) << 4));
   *reinterpret_cast<uint4*>(e.gA + off) = hi;
   *reinterpret_cast<uint4*>(e.gA + off + kT2APart) = lo;
+  if (!arrive) return;
   // one arrival per warp on the leader's hand-off barrier of this round (k-chunks j and 4 + j) of tile t
   fence_proxy_async();
   tc_fence_before();
@@ -239,7 +242,7 @@ __device__ __forceinline__ bool t2_epi(const TcArgs& a, const T2Epi& e, int t, i
         }
       }
     }
-    if (KIND != 3 && store_a) t2_store_a(e, t, n0, j, out);
+    if (KIND != 3 && store_a) t2_store_a(e, t, n0, e.coarse ? 0 : j, !e.coarse || j == 3, out);
   }
   return true;
 }
@@ -349,7 +352,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
             const uint32_t aT = sA + t * kT2ATile;
             for (int si = 0; si < nst; ++si) {
               const int c = (nst == 8) ? ((si >> 1) + 4 * (si & 1)) : si;
-              if ((si & 1) == 0) {  // one hand-off barrier per epilogue round: chunks j and 4 + j (layer 0: chunks 0, 1)
+              if ((si & 1) == 0 && (si == 0 || !(a.dbg & 32))) {  // one hand-off barrier per epilogue round: chunks j and 4 + j
+                // (layer 0: chunks 0, 1; coarse mode: one barrier per tile-step)
                 const int bi = t * 4 + (si >> 1);
                 if (!__all_sync(0xffffffffu, mbar_wait2t(bAReady + 8 * bi, (a_par >> bi) & 1, a.err, 2, abort_flag, prof, tp1))) goto tc2_done;
                 a_par ^= (1u << bi);
@@ -395,6 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     e.d_full = bDFull;
     e.abort_flag = abort_flag;
     e.prof = prof;
+    e.coarse = (a.dbg & 32) != 0;
     const int w8 = e.qh * 4 + e.sub;  // index among the 8 warps that share this thread's row
     uint32_t d_par = 0;               // bit t*2+b = parity to wait for on d_full[t][b]
     for (int su = cluster_id; su < n_super; su += n_clusters) {
@@ -409,7 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
         float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(e.qh * 32 + e.sub * 8 + i, 0, px, py, pz, a.embed_w);
-        t2_store_a(e, t, e.qh * 32 + e.sub * 8, 0, x);
+        t2_store_a(e, t, e.qh * 32 + e.sub * 8, 0, true, x);
       }
       float ha0 = 0.f, ha1 = 0.f, ha2 = 0.f, ha3 = 0.f, hb0 = 0.f, hb1 = 0.f, hb2 = 0.f, hb3 = 0.f;
       bool ok = true;
