@@ -242,8 +242,8 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
 // Hand-node variant of k_inverse_warp<true, true> that walks `kSeg` consecutive samples of one ray per thread and
 // seeds each sample's KNN from the previous one (knn15_seeded).  Same arithmetic, same results.
 constexpr int kSeg = 32;
-__global__ void __launch_bounds__(128)
-k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
+__device__ __forceinline__ void
+inverse_warp_hand_rays_body(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
                          const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
                          const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
                          const SamplerState* __restrict__ st) {
@@ -280,6 +280,20 @@ k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* _
     xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
     xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
   }
+}
+
+__global__ void __launch_bounds__(128)
+k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
+                         const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
+                         const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
+  inverse_warp_hand_rays_body(rays_per_frame, ns, zstride, zbuf, cam, dirs, tfs, verts, skin_w, xc, st);
+}
+// HOLD_KNN_OCC=1 (round-2 A/B): the same body compiled for >= 6 resident blocks per SM (<= 85 registers)
+__global__ void __launch_bounds__(128, 6)
+k_inverse_warp_hand_rays_occ(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
+                             const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
+                             const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
+  inverse_warp_hand_rays_body(rays_per_frame, ns, zstride, zbuf, cam, dirs, tfs, verts, skin_w, xc, st);
 }
 
 // extract_features' normal (engine/volsdf_utils.py:66-102): J = d x_d / d x_c of forward skinning with detached
