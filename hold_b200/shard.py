@@ -18,3 +18,52 @@ def shard_range(n: int, rank: int, world: int, align: int = 512) -> tuple[int, i
 def shard_frames(n_frames: int, rank: int, world: int) -> list[int]:
     """Round-robin frames, the reference's own `--agent_id` farming idea (datasets/eval_datasets.py:43-50)."""
     return list(range(rank, n_frames, world))
+
+
+def allreduce_flat_(tensors, group=None, average: bool = False):
+    """ONE all-reduce (sum) over a single flat bucket holding every tensor of `tensors` — the "single NCCL all-reduce on
+    gradients per step" of the north star / SURVEY §8e for data-parallel steps (frame-sharded pose refinement,
+    optimize_ckpt.py: shared parameters — betas, scene_scale, obj_scale — receive gradient terms from every rank's frames;
+    per-frame parameters stay local).  In place; `None` entries are skipped.  Backend-agnostic plumbing
+    (torch.distributed: nccl on the GPU box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    ts = [t for t in tensors if t is not None]
+    if not ts or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in ts])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    o = 0
+    for t in ts:
+        n = t.numel()
+        t.copy_(flat[o:o + n].view_as(t))
+        o += n
+    return tensors
+
+
+def allreduce_grads_(params, group=None, average: bool = False):
+    """`allreduce_flat_` over the `.grad` of parameters (those that have one)."""
+    allreduce_flat_([p.grad for p in params if p.grad is not None], group=group, average=average)
+
+
+def gather_rays(local, n_total: int, rank: int, world: int, align: int = 512, group=None, dst: int = 0):
+    """Assemble a per-ray output ([n_local, ...] on every rank, shards from `shard_range`) on rank `dst`: the only
+    collective of a sharded render, and only for image assembly.  Returns the full [n_total, ...] tensor on
+    `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    sizes = [shard_range(n_total, r, world, align) for r in range(world)]
+    pad = max(e - s for s, e in sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([o[: e - s] for o, (s, e) in zip(out, sizes)], 0)

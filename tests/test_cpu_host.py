@@ -74,7 +74,16 @@ def _gloo_worker(rank, world, port, q):
     dist.all_reduce(mine)                       # every ray owned by exactly one rank
     t = torch.tensor([float(e - s)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)    # the bench's max-over-ranks reduction
-    q.put((rank, bool((mine == 1).all()), t.item()))
+    # one flat-bucket all-reduce over several gradient tensors (frame-sharded pose refinement)
+    from hold_b200.shard import allreduce_flat_, gather_rays
+    g1, g2 = torch.full((10,), float(rank + 1)), torch.full((2, 3), 10.0 * (rank + 1))
+    allreduce_flat_([g1, None, g2])
+    ok_ar = bool((g1 == 3.0).all() and (g2 == 30.0).all())
+    # image assembly on rank 0
+    local = torch.arange(s, e, dtype=torch.float32)[:, None].repeat(1, 3)
+    full = gather_rays(local, n, rank, world)
+    ok_g = (full is None) if rank != 0 else bool(torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32)))
+    q.put((rank, bool((mine == 1).all()) and ok_ar and ok_g, t.item()))
     dist.destroy_process_group()
 
 
