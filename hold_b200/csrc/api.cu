@@ -13,6 +13,7 @@
 #include "composite.cuh"
 #include "background.cuh"
 #include "pose_bwd.cuh"
+#include "mesh_sdf.cuh"
 
 namespace hold {
 
@@ -637,6 +638,29 @@ int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, in
     if (rc) return rc;
   }
   return hold_composite(ctx, n, R, S, factors, cls, comp, per_node, stream);
+}
+
+int hold_mesh_sdf(hold_ctx* ctx, int B, int P, const float* points, int V, const float* verts, int verts_batched, int F,
+                  const int32_t* faces, float* sdf, int32_t* face_idx, void* stream) {
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_REQUIRE(B >= 0 && P >= 0 && V > 0 && F > 0, "bad sizes");
+  if (B == 0 || P == 0) return HOLD_OK;
+  HOLD_REQUIRE(points && verts && faces && sdf, "NULL argument");
+  dim3 grid(ceil_div(P, 128), B);
+  k_mesh_sdf<<<grid, 128, 0, (cudaStream_t)stream>>>(P, V, F, verts_batched ? V * 3 : 0, points, verts, faces, sdf, face_idx);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float threshold, uint8_t* off_surface,
+                        uint8_t* in_surface, void* stream) {
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_REQUIRE(R >= 0 && S >= 1, "bad sizes");
+  if (R == 0) return HOLD_OK;
+  HOLD_REQUIRE(sdf != nullptr, "NULL argument");
+  k_off_in_surface<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(R, S, sdf, threshold, off_surface, in_surface);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
 }
 
 /* debug/test hook (not in the public header): workspace slot pointers of the last call */

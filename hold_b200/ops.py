@@ -71,3 +71,27 @@ def inverse_warp(node, x, pose: NodePose, want_idx=False):
     mask = torch.empty(B, P, dtype=torch.uint8, device=x.device) if want_idx else None
     check(lib().hold_inverse_warp(node.ctx.h, node.slot, B, P, ptr(x.float().contiguous()), C.byref(pose), ptr(xc), ptr(idx), ptr(mask), stream_ptr()))
     return xc, idx, mask
+
+
+def compute_mano_cano_sdf(ctx, mesh_v_cano, mesh_f_cano, x_cano):
+    """engine/volsdf_utils.py:172-186 without kaolin: signed distance [B,P] of x_cano [B,P,3] to the closed mesh
+    (mesh_v_cano [B,V,3] or [V,3]; mesh_f_cano [F,3] integer)."""
+    x = x_cano.detach().float().contiguous()
+    B, P, _ = x.shape
+    v = mesh_v_cano.detach().float().contiguous()
+    batched = v.dim() == 3 and v.shape[0] == B and B > 1
+    if v.dim() == 3 and not batched:
+        v = v[0].contiguous()
+    f = mesh_f_cano.to(torch.int32).contiguous()
+    out = torch.empty(B, P, device=x.device)
+    check(lib().hold_mesh_sdf(ctx.h, B, P, ptr(x), v.shape[-2], ptr(v), int(batched), f.shape[0], ptr(f), ptr(out), None, stream_ptr()))
+    return out
+
+
+def check_off_in_surface_points_cano_mesh(ctx, mesh_v_cano, mesh_f_cano, x_cano, num_pixels_total, threshold=0.05):
+    """engine/volsdf_utils.py:189-217: (index_off_surface, index_in_surface), bool [num_pixels_total]."""
+    sd = compute_mano_cano_sdf(ctx, mesh_v_cano, mesh_f_cano, x_cano).reshape(num_pixels_total, -1).contiguous()
+    off = torch.empty(num_pixels_total, dtype=torch.uint8, device=sd.device)
+    inn = torch.empty_like(off)
+    check(lib().hold_off_in_surface(ctx.h, num_pixels_total, sd.shape[1], ptr(sd), float(threshold), ptr(off), ptr(inn), stream_ptr()))
+    return off.bool(), inn.bool()

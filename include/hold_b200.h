@@ -161,6 +161,16 @@ int hold_mano_lbs_bwd(hold_ctx* ctx, const hold_mano_model* m, int B, const floa
 int hold_object_tf_bwd(hold_ctx* ctx, int B, const float* rot, const float* trans, const float* scene_scale, float obj_scale,
                        const float* denorm_mat, const float* pts_cano, int Nv, const float* g_verts, const float* g_tfs,
                        float* g_rot, float* g_trans, float* g_scene_scale, float* g_obj_scale, void* stream);
+/* Training-only loss targets — replaces the reference's kaolin v0.10.0 calls in
+ * compute_mano_cano_sdf / check_off_in_surface_points_cano_mesh (engine/volsdf_utils.py:172-217):
+ * sdf[b,p] = sqrt(point_to_mesh_distance) * (1 - 2 * check_sign) of points [B,P,3] against the closed mesh
+ * (verts [B,V,3] if verts_batched else [V,3] shared by all frames; faces [F,3] int32).  face_idx (nullable) = nearest face. */
+int hold_mesh_sdf(hold_ctx* ctx, int B, int P, const float* points, int V, const float* verts, int verts_batched, int F,
+                  const int32_t* faces, float* sdf, int32_t* face_idx, void* stream);
+/* The per-ray reduction of check_off_in_surface_points_cano_mesh (volsdf_utils.py:209-217): over the S samples of each of
+ * R rays, off_surface = min sdf > threshold, in_surface = min sdf <= 0 (uint8 flags, each output nullable). */
+int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float threshold, uint8_t* off_surface,
+                        uint8_t* in_surface, void* stream);
 /* a17: ObjectModel.forward (model/obj/object_model.py:29-70). */
 int hold_object_tf(hold_ctx* ctx, int B, const float* rot /*[B,3]*/, const float* trans /*[B,3]*/,
                    const float* scene_scale /*[B]*/, float obj_scale, const float* denorm_mat /*[4,4]*/,
