@@ -14,6 +14,7 @@
 #include "background.cuh"
 #include "pose_bwd.cuh"
 #include "mesh_sdf.cuh"
+#include "mise.cuh"
 
 namespace hold {
 
@@ -660,6 +661,104 @@ int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float thr
   HOLD_REQUIRE(sdf != nullptr, "NULL argument");
   k_off_in_surface<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(R, S, sdf, threshold, off_surface, in_surface);
   HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_mise_destroy(hold_mise* h) {
+  if (!h) return HOLD_OK;
+  cudaFree(h->g.val), cudaFree(h->g.state), cudaFree(h->queue), cudaFree(h->counter);
+  for (int L = 0; L < mise::kMaxDepth; ++L) { cudaFree(h->g.sub[L]); cudaFree(h->g.mark[L]); }
+  delete h;
+  return HOLD_OK;
+}
+
+int hold_mise_create(hold_ctx* ctx, int resolution_0, int depth, float threshold, hold_mise** out, void* stream) {
+  HOLD_REQUIRE(ctx && out, "NULL argument");
+  HOLD_REQUIRE(resolution_0 >= 1 && depth >= 0 && depth <= mise::kMaxDepth, "bad MISE shape");
+  HOLD_REQUIRE(((long long)resolution_0 << depth) <= 1024, "MISE resolution above 1024 is not supported");
+  hold_mise* h = new (std::nothrow) hold_mise();
+  HOLD_REQUIRE(h != nullptr, "out of host memory");
+  h->ctx = ctx;
+  mise::Grid& g = h->g;
+  memset(&g, 0, sizeof(g));
+  g.res0 = resolution_0, g.depth = depth, g.R = resolution_0 << depth, g.G = g.R + 1, g.threshold = threshold;
+  h->np = (size_t)g.G * g.G * g.G;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMalloc((void**)&g.val, h->np * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&g.state, h->np);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->queue, h->np * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->counter, sizeof(unsigned int));
+  for (int L = 0; L < depth && e == cudaSuccess; ++L) {
+    const size_t n = (size_t)(resolution_0 << L) * (resolution_0 << L) * (resolution_0 << L);
+    e = cudaMalloc((void**)&g.sub[L], n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g.mark[L], n * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.sub[L], 0, n, s);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(g.val, 0, h->np * sizeof(float), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g.state, 0, h->np, s);
+  if (e != cudaSuccess) {
+    set_error("hold_mise_create: %s", cudaGetErrorString(e));
+    hold_mise_destroy(h);
+    return HOLD_E_CUDA;
+  }
+  const int n0 = (resolution_0 + 1) * (resolution_0 + 1) * (resolution_0 + 1);
+  k_mise_init<<<ceil_div(n0, 256), 256, 0, s>>>(g);
+  HOLD_LAUNCH_CHECK(ctx);
+  *out = h;
+  return HOLD_OK;
+}
+
+int hold_mise_query(hold_mise* h, int32_t* coords, int capacity, int* n_points, void* stream) {
+  HOLD_REQUIRE(h && n_points, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  HOLD_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), s));
+  k_mise_collect<<<h->ctx->sm_count * 8, 256, 0, s>>>(h->g, h->queue, h->counter, (unsigned int)h->np);
+  HOLD_LAUNCH_CHECK(h->ctx);
+  unsigned int n = 0;
+  HOLD_CUDA(cudaMemcpyAsync(&n, h->counter, sizeof(n), cudaMemcpyDeviceToHost, s));
+  HOLD_CUDA(cudaStreamSynchronize(s));   // the caller sizes its SDF query by n: one host sync per MISE round, as in the reference loop
+  h->n_last = (int)n;
+  *n_points = (int)n;
+  if (n == 0 || coords == nullptr) return HOLD_OK;
+  HOLD_REQUIRE(capacity >= (int)n, "coords buffer holds %d points, %u needed", capacity, n);
+  k_mise_coords<<<ceil_div((int)n, 256), 256, 0, s>>>(h->g, h->queue, (int)n, coords);
+  HOLD_LAUNCH_CHECK(h->ctx);
+  return HOLD_OK;
+}
+
+int hold_mise_update(hold_mise* h, const float* values, int n_values, void* stream) {
+  HOLD_REQUIRE(h && (values || n_values == 0), "NULL argument");
+  HOLD_REQUIRE(n_values == h->n_last, "update with %d values after a query of %d points", n_values, h->n_last);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_values > 0) {
+    k_mise_scatter<<<ceil_div(n_values, 256), 256, 0, s>>>(h->g, h->queue, n_values, values);
+    HOLD_LAUNCH_CHECK(h->ctx);
+  }
+  h->n_last = 0;
+  const mise::Grid& g = h->g;
+  for (int L = 0; L < g.depth; ++L) {
+    const size_t n = (size_t)(g.res0 << L) * (g.res0 << L) * (g.res0 << L);
+    HOLD_CUDA(cudaMemsetAsync(g.mark[L], 0, n * sizeof(unsigned int), s));
+  }
+  if (g.depth == 0) return HOLD_OK;
+  k_mise_mark<<<h->ctx->sm_count * 8, 256, 0, s>>>(g);
+  HOLD_LAUNCH_CHECK(h->ctx);
+  for (int L = 0; L < g.depth; ++L) {
+    k_mise_subdivide<<<h->ctx->sm_count * 4, 256, 0, s>>>(g, L);
+    HOLD_LAUNCH_CHECK(h->ctx);
+  }
+  return HOLD_OK;
+}
+
+int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
+  HOLD_REQUIRE(h && out, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_mise_dense_init<<<h->ctx->sm_count * 8, 256, 0, s>>>(h->g, out);
+  HOLD_LAUNCH_CHECK(h->ctx);
+  for (int axis = 0; axis < 3; ++axis) {
+    k_mise_fill<<<ceil_div(h->g.G * h->g.G, 128), 128, 0, s>>>(h->g, out, axis);
+    HOLD_LAUNCH_CHECK(h->ctx);
+  }
   return HOLD_OK;
 }
 

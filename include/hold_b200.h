@@ -171,6 +171,20 @@ int hold_mesh_sdf(hold_ctx* ctx, int B, int P, const float* points, int V, const
  * R rays, off_surface = min sdf > threshold, in_surface = min sdf <= 0 (uint8 flags, each output nullable). */
 int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float threshold, uint8_t* off_surface,
                         uint8_t* in_surface, void* stream);
+/* GPU Multiresolution IsoSurface Extraction — the class `mise.MISE` of code/src/libmise/mise.pyx (the
+ * reference's only native code) as driven by generate_mesh (utils/meshing.py:9-72): same query / update / to_dense rounds,
+ * same dense (R+1)^3 value grid, R = resolution_0 << depth, bit for bit; marching cubes stays with the caller (skimage).
+ *   create   : MISE.__cinit__ (mise.pyx:47-88)
+ *   query    : MISE.query  -> lattice coordinates [n,3] int32 of the points without a value (device buffer `coords` of
+ *              `capacity` points, may be NULL to only count); *n_points on the host (one stream sync per round)
+ *   update   : MISE.update -> values [n] in the order of the last query; marks and subdivides active voxels
+ *   to_dense : MISE.to_dense -> out [(R+1)^3] float32, x-major like the reference's array */
+typedef struct hold_mise hold_mise;
+int hold_mise_create(hold_ctx* ctx, int resolution_0, int depth, float threshold, hold_mise** out, void* stream);
+int hold_mise_query(hold_mise* h, int32_t* coords, int capacity, int* n_points, void* stream);
+int hold_mise_update(hold_mise* h, const float* values, int n_values, void* stream);
+int hold_mise_to_dense(hold_mise* h, float* out, void* stream);
+int hold_mise_destroy(hold_mise* h);
 /* a17: ObjectModel.forward (model/obj/object_model.py:29-70). */
 int hold_object_tf(hold_ctx* ctx, int B, const float* rot /*[B,3]*/, const float* trans /*[B,3]*/,
                    const float* scene_scale /*[B]*/, float obj_scale, const float* denorm_mat /*[4,4]*/,
