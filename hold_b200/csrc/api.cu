@@ -385,12 +385,8 @@ int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* b
     d.tips[i] = m->tip_ids_host[i];
     HOLD_REQUIRE(d.tips[i] >= 0 && d.tips[i] < kVerts, "tip id out of range");
   }
-  static bool attr_set = false;
-  const int smem = (2 * kVerts * 3 + kJoints * 3 + kJoints * 9 + 136 + 2 * kJoints * 16 + 16) * (int)sizeof(float);
-  if (!attr_set) {
-    HOLD_CUDA(cudaFuncSetAttribute(k_mano_lbs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  constexpr int smem = (2 * kVerts * 3 + kJoints * 3 + kJoints * 9 + 136 + 2 * kJoints * 16 + 16) * (int)sizeof(float);
+  static_assert(smem <= 48 * 1024, "k_mano_lbs fits the default dynamic shared memory limit (no per-device attribute needed)");
   k_mano_lbs<<<B, 256, smem, (cudaStream_t)stream>>>(d, betas, full_pose, transl, scene_scale, tfs_c_inv, verts, jnts, tfs, v_posed);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
@@ -417,11 +413,7 @@ int hold_mano_lbs_bwd(hold_ctx* ctx, const hold_mano_model* m, int B, const floa
     HOLD_REQUIRE(d.tips[i] >= 0 && d.tips[i] < kVerts, "tip id out of range");
   }
   const int nt = 256, smem = posebwd::mano_scratch_floats(nt) * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    HOLD_CUDA(cudaFuncSetAttribute(k_mano_lbs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  HOLD_REQUIRE(smem <= 48 * 1024, "k_mano_lbs_bwd scratch exceeds the default dynamic shared memory limit");
   k_mano_lbs_bwd<<<B, nt, smem, (cudaStream_t)stream>>>(d, betas, full_pose, transl, scene_scale, tfs_c_inv, g_verts, g_jnts, g_tfs,
                                                         g_betas, g_pose, g_transl, g_scale);
   HOLD_LAUNCH_CHECK(ctx);
