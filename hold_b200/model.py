@@ -263,6 +263,10 @@ class Node(nn.Module):
         else:
             self.server = ObjectServer(ctx, obj_pts)
             self.frame_latent_encoder = nn.Embedding(n_frames, 32)
+        # per-frame pose parameters, same module names as the reference (model/generic/params.py) so that a reference
+        # checkpoint loads (hold_b200/checkpoint.py); used when the input dict carries only frame ids
+        from .checkpoint import HAND_PARAMS, OBJECT_PARAMS, GenericParams
+        self.params = GenericParams(n_frames, HAND_PARAMS if self.kind == "hand" else OBJECT_PARAMS, node_id)
         self.mlp_mode = mlp_mode
         self.configure()
         self.S = sampler_cfg["N_samples"] + sampler_cfg["N_samples_extra"] + 2
@@ -298,6 +302,10 @@ class Node(nn.Module):
     def articulate(self, input):
         """The server call at the top of sample_points (mano_node.py:72-79 / object_node.py:58-62) -> NodePose."""
         nid = self.node_id
+        if f"{nid}.transl" not in input:   # only frame ids given: the node's own per-frame parameters (hold.py: params(idx))
+            input = {**input, **self.params(input["idx"])}
+            if self.kind == "hand":
+                input[f"{nid}.full_pose"] = torch.cat([input[f"{nid}.global_orient"], input[f"{nid}.pose"]], 1)
         scale = input[f"{nid}.params"][:, 0]
         pose = NodePose()
         keep = []

@@ -99,3 +99,52 @@ def test_world_size_2_gloo():
     [p.join(60) for p in ps]
     assert all(ok for _, ok, _ in res) and all(p.exitcode == 0 for p in ps)
     assert {r for r, _, _ in res} == {0, 1}
+
+
+def test_reference_checkpoint_key_mapping():
+    """hold_b200.checkpoint: a state_dict laid out like the reference's (hold/hold.py + hold_net.py naming) loads into modules
+    with the mirror's names; server / deformer buffers are ignored; strictness is on OUR keys."""
+    import torch.nn as nn
+
+    from hold_b200 import checkpoint as ck
+    from hold_b200 import synth
+    from hold_b200.model import ImplicitNet, LaplaceDensity, RenderingNet
+
+    class FakeNode(nn.Module):           # the mirror Node's learnable sub-modules, without a device context
+        def __init__(self, kind, n_frames):
+            super().__init__()
+            self.implicit_network, self.rendering_network, self.density = ImplicitNet(kind), RenderingNet(kind), LaplaceDensity()
+            self.params = ck.GenericParams(n_frames, ck.HAND_PARAMS if kind == "hand" else ck.OBJECT_PARAMS, "right" if kind == "hand" else "object")
+            if kind == "object":
+                self.frame_latent_encoder = nn.Embedding(n_frames, 32)
+
+    class FakeNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.nodes = nn.ModuleDict({"right": FakeNode("hand", 7), "object": FakeNode("object", 7)})
+            self.synced = 0
+
+        def sync_weights(self):
+            self.synced += 1
+
+    # a "reference" state dict: same tensors under model.*, plus buffers the mirror must ignore
+    src = FakeNet()
+    for nid, kind in (("right", "hand"), ("object", "object")):
+        src.nodes[nid].implicit_network.load_state_dict(synth.make_sdf_state(kind, 3, 0.5))
+        src.nodes[nid].rendering_network.load_state_dict(synth.make_rgb_state(kind, 3))
+        src.nodes[nid].params.global_orient.weight.data.normal_()
+    sd = {"model." + k: v.clone() for k, v in src.state_dict().items()}
+    sd["model.nodes.right.server.verts_c"] = torch.zeros(1, 778, 3)
+    sd["model.nodes.object.server.object_model.v3d_cano"] = torch.zeros(10, 3)
+    sd["model.nodes.object.implicit_network.embedder_obj.alpha_iter"] = torch.tensor(5)
+    sd["loss.some_buffer"] = torch.zeros(1)
+    dst = FakeNet()
+    info = ck.load_reference_state_dict(dst, sd)
+    assert dst.synced == 1 and not info["missing"] and len(info["ignored"]) == 4
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    p = dst.nodes["right"].params(torch.tensor([0, 3]))
+    assert set(p) == {"right.global_orient", "right.pose", "right.transl", "right.betas"} and p["right.betas"].shape == (2, 10)
+    del sd["model.nodes.right.density.beta"]
+    with pytest.raises(KeyError):
+        ck.load_reference_state_dict(FakeNet(), sd)
