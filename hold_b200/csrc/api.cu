@@ -133,7 +133,9 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
     const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
     dim3 g2(ceil_div(rays * segs, 128), B);
     static const bool knn_occ = [] { const char* e = getenv("HOLD_KNN_OCC"); return e != nullptr && atoi(e) != 0; }();
-    if (knn_occ) k_inverse_warp_hand_rays_occ<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
+    static const bool knn_filt = [] { const char* e = getenv("HOLD_KNN_FILTER"); return e != nullptr && atoi(e) != 0; }();
+    if (knn_filt) k_inverse_warp_hand_rays_filt<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
+    else if (knn_occ) k_inverse_warp_hand_rays_occ<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     else k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     HOLD_LAUNCH_CHECK(ctx);
     return HOLD_OK;

@@ -2,6 +2,7 @@
 // KNN-weighted inverse / forward skinning (a6), rigid warp (a7), normals from the skinning Jacobian (a10).
 #pragma once
 #include "common.cuh"
+#include "knn_phases.h"
 
 namespace hold {
 
@@ -294,6 +295,64 @@ k_inverse_warp_hand_rays_occ(int rays_per_frame, int ns, int zstride, const floa
                              const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
                              const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
   inverse_warp_hand_rays_body(rays_per_frame, ns, zstride, zbuf, cam, dirs, tfs, verts, skin_w, xc, st);
+}
+
+// HOLD_KNN_FILTER=1 (round-2 A/B): the same walk with the filtered exact KNN of knn_phases.h (one 16-byte shared load + 3 FMA per
+// vertex in the scan instead of 3 loads + 9 instructions; bit-identical neighbours, tests/test_cpu_knn_filter.py).
+__global__ void __launch_bounds__(128)
+k_inverse_warp_hand_rays_filt(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
+                              const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
+                              const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
+  if (st != nullptr && st->done) return;
+  __shared__ knnf::V4 sv4[kVerts];
+  __shared__ float stf[kJoints * 16];
+  __shared__ unsigned short scand[128 * knnf::kCand];
+  __shared__ float s_qmax;
+  unsigned short* cand = scand + threadIdx.x * knnf::kCand;
+  const int b = blockIdx.y;
+  for (int v = threadIdx.x; v < kVerts; v += blockDim.x) {
+    const float* pv = verts + ((size_t)b * kVerts + v) * 3;
+    knnf::V4 e;
+    e.x = pv[0], e.y = pv[1], e.z = pv[2];
+    e.q = e.x * e.x + e.y * e.y + e.z * e.z;
+    sv4[v] = e;
+  }
+  for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float q = 0.f;
+    for (int v = 0; v < kVerts; ++v) q = fmaxf(q, sv4[v].q);
+    s_qmax = q;
+  }
+  __syncthreads();
+  const float qmax = s_qmax;
+  const int segs = (ns + kSeg - 1) / kSeg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rays_per_frame * segs) return;
+  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
+  const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
+  const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+  knnf::Top top;
+  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
+  for (int k = k0; k < k1; ++k) {
+    const float tz = zbuf[ray * zstride + k];
+    const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
+    if (k == k0) knnf::full_scan(sv4, x, y, z, top);
+    else knnf::seeded_filter(sv4, qmax, x, y, z, top, cand);
+    Knn15 nn;
+#pragma unroll
+    for (int j = 0; j < kKnn; ++j) { nn.d[j] = top.d[j]; nn.i[j] = top.i[j]; }
+    float T[12], s, dmin;
+    blend_tf(nn, skin_w, stf, T, s, dmin);
+    float Ai[9];
+    inv3(T, 4, Ai);
+    const float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
+    const size_t gp = ray * ns + k;
+    xc[3 * gp] = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
+    xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
+    xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
+  }
 }
 
 // extract_features' normal (engine/volsdf_utils.py:66-102): J = d x_d / d x_c of forward skinning with detached
