@@ -87,7 +87,8 @@ struct TcArgs {
   const SamplerState* st;
   int* err;
   int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too,
-            // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel)
+            // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel),
+            // 32 = coarse hand-offs (pair kernel), 64 = LEAN reverse mode stashes t and computes softplus' in the backward rounds
   long long* prof;  // pair kernel, HOLD_TC_PROF=1: cycle accounting of cluster 0 (see mlp_tc2.cuh)
 };
 
@@ -223,6 +224,13 @@ __device__ __forceinline__ float softplus_t(float t, float& u_out) {
   const float u = mufu_ex2(-fabsf(t));
   u_out = u;
   return fmaxf(t, 0.f) + mufu_lg2(1.0f + u);
+}
+
+// softplus'(z) = sigmoid(100 z) from t = 100 z log2(e): 2^t / (1 + 2^t), overflow-free
+__device__ __forceinline__ float sigmoid_t(float t) {
+  const float u = mufu_ex2(-fabsf(t));
+  const float r = mufu_rcp(1.0f + u);
+  return (t >= 0.f) ? r : u * r;
 }
 
 // One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
@@ -500,8 +508,12 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
                   z = acc[i] + bv[i];
                   out[i] = softplus100_fast(z, e);
                 }
-                const float r = mufu_rcp(1.0f + e);
-                sg[i] = (z >= 0.f) ? r : e * r;
+                if (LEAN && (a.dbg & 64)) {
+                  sg[i] = z;   // stash t; softplus' is computed where it is consumed (backward rounds: idle MUFU pipe)
+                } else {
+                  const float r = mufu_rcp(1.0f + e);
+                  sg[i] = (z >= 0.f) ? r : e * r;
+                }
               }
               *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0) = make_float4(sg[0], sg[1], sg[2], sg[3]);
               *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0 + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
@@ -524,8 +536,12 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
                 dst[0] = make_float4(fmaf(acc[0], fs, bv[0]), fmaf(acc[1], fs, bv[1]), fmaf(acc[2], fs, bv[2]), fmaf(acc[3], fs, bv[3]));
                 dst[1] = make_float4(fmaf(acc[4], fs, bv[4]), fmaf(acc[5], fs, bv[5]), fmaf(acc[6], fs, bv[6]), fmaf(acc[7], fs, bv[7]));
               }
-              const float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0);
-              const float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0 + 4);
+              float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0);
+              float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0 + 4);
+              if (LEAN && (a.dbg & 64)) {
+                s0 = make_float4(sigmoid_t(s0.x), sigmoid_t(s0.y), sigmoid_t(s0.z), sigmoid_t(s0.w));
+                s1 = make_float4(sigmoid_t(s1.x), sigmoid_t(s1.y), sigmoid_t(s1.z), sigmoid_t(s1.w));
+              }
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
               const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
               // g_7 = w_sdf * s_7, times the operand scale (LEAN: a.w_last holds w_sdf * ln2/100)
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               out[4] = ks * w1.x * s1.x, out[5] = ks * w1.y * s1.y, out[6] = ks * w1.z * s1.z, out[7] = ks * w1.w * s1.w;
             } else if (kind == 2) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) out[i] = kTcScaleA * acc[i] * bv[i];
+              for (int i = 0; i < 8; ++i) out[i] = kTcScaleA * acc[i] * ((LEAN && (a.dbg & 64)) ? sigmoid_t(bv[i]) : bv[i]);
               if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

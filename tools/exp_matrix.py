@@ -10,6 +10,7 @@ from hold_b200 import capi, scene_io, synth
 VARIANTS = [
     ("single-CTA (default)", dict()),
     ("single-CTA LEAN", dict(HOLD_TC_LEAN="1")),
+    ("single-CTA LEAN, t-stash", dict(HOLD_TC_LEAN="1", HOLD_TC_DBG="64")),
     ("pair fine hand-offs", dict(HOLD_TC_PAIR="1")),
     ("pair coarse hand-offs", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="32")),
 ]
