@@ -12,6 +12,7 @@
 #include "mlp_tc2.cuh"
 #include "composite.cuh"
 #include "background.cuh"
+#include "background_tc.cuh"
 #include "pose_bwd.cuh"
 #include "mesh_sdf.cuh"
 #include "mise.cuh"
@@ -195,6 +196,7 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
   if (rc == HOLD_OK) rc = tc2_init();
+  if (rc == HOLD_OK) rc = tc_bg_init();
   if (rc) { delete ctx; return rc; }
   *out = ctx;
   return HOLD_OK;
@@ -219,6 +221,7 @@ int hold_ctx_destroy(hold_ctx* ctx) {
     if (ns.sstate) cudaFree(ns.sstate);
     tc_free(ns);
   }
+  tc_bg_free(ctx->bg_tc);
   for (int l = 0; l < HOLD_MAX_LAYERS; ++l) {
     if (ctx->bg_sdf.Wt[l]) cudaFree(ctx->bg_sdf.Wt[l]);
     if (ctx->bg_sdf.bias[l]) cudaFree(ctx->bg_sdf.bias[l]);
@@ -802,6 +805,8 @@ int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_m
   if ((rc = dev_alloc(&c.b_last, 4))) return rc;
   k_pack_rows<<<3, 128, 0, s>>>(rgb->weight_v[1], rgb->weight_g[1], rgb->bias[1], 128, 0, 3, c.w_last, c.b_last);
   HOLD_LAUNCH_CHECK(ctx);
+  { const char* e = getenv("HOLD_BG_TC");   // tcgen05 images only for the experimental path
+    if (e != nullptr && atoi(e) != 0 && (rc = tc_bg_pack(ctx, ctx->bg_tc, sdf, rgb, s))) return rc; }
   ctx->has_bg = true;
   return HOLD_OK;
 }
@@ -837,15 +842,21 @@ int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const flo
       a.n_layers = 9;
       for (int l = 0; l < 9; ++l) { a.L[l].Wt = ctx->bg_sdf.Wt[l], a.L[l].bias = ctx->bg_sdf.bias[l], a.L[l].Kpad = ctx->bg_sdf.Kpad[l], a.L[l].N = ctx->bg_sdf.N[l]; }
       a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last, a.sdf = sdf_ws, a.feat = feat_ws;
-      const int tiles = ceil_div(P, kTileRows);
-      k_bg_mlp<BG_SDF><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(a);
-      HOLD_LAUNCH_CHECK(ctx);
-      BgArgs c = a;
-      c.n_layers = 1;
-      c.L[0].Wt = ctx->bg_rgb.Wt[0], c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].Kpad = ctx->bg_rgb.Kpad[0], c.L[0].N = 128;
-      c.w_last = ctx->bg_rgb.w_last, c.b_last = ctx->bg_rgb.b_last, c.rgb = rgb_ws;
-      k_bg_mlp<BG_RGB><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(c);
-      HOLD_LAUNCH_CHECK(ctx);
+      static const bool bg_tc = [] { const char* e = getenv("HOLD_BG_TC"); return e != nullptr && atoi(e) != 0; }();
+      if (bg_tc && ctx->bg_tc != nullptr) {
+        int rc = tc_bg_launch(ctx, *ctx->bg_tc, P, a.cam, a.dirs, a.frame_code, a.r_sphere, sdf_ws, feat_ws, rgb_ws, s);
+        if (rc) return rc;
+      } else {
+        const int tiles = ceil_div(P, kTileRows);
+        k_bg_mlp<BG_SDF><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(a);
+        HOLD_LAUNCH_CHECK(ctx);
+        BgArgs c = a;
+        c.n_layers = 1;
+        c.L[0].Wt = ctx->bg_rgb.Wt[0], c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].Kpad = ctx->bg_rgb.Kpad[0], c.L[0].N = 128;
+        c.w_last = ctx->bg_rgb.w_last, c.b_last = ctx->bg_rgb.b_last, c.rgb = rgb_ws;
+        k_bg_mlp<BG_RGB><<<min(tiles, ctx->sm_count), 256, kBgSmemBytes, s>>>(c);
+        HOLD_LAUNCH_CHECK(ctx);
+      }
       k_bg_composite<<<ceil_div(rn, 128), 128, 0, s>>>(rn, a.r_sphere, sdf_ws, rgb_ws, fg_bg_weights + ray0,
                                                        bg_rgb ? bg_rgb + ray0 * 3 : nullptr, bg_rgb_only ? bg_rgb_only + ray0 * 3 : nullptr,
                                                        bg_semantics ? bg_semantics + ray0 * 4 : nullptr, bg_z_vals ? bg_z_vals + ray0 * kBgN : nullptr);

@@ -42,6 +42,7 @@ struct PackedMlp {           // fp32 CUDA-core layout: Wt[l] is [Kpad][Npad] (k-
 };
 
 struct TcMlp;  // tcgen05 packing, mlp_tc.cuh
+struct TcBg;   // tcgen05 packing of the background nets, background_tc.cuh
 
 struct NodeState {
   bool configured = false, has_weights = false, has_rig = false;
@@ -71,6 +72,7 @@ struct hold_ctx {
   hold::Buffer ws[24];  // grow-only workspaces, indexed by purpose (api.cu)
   hold::PackedMlp bg_sdf, bg_rgb;  // background nets (fp32 CUDA-core layout)
   bool has_bg = false;
+  hold::TcBg* bg_tc = nullptr;
 };
 
 namespace hold {
@@ -114,6 +116,43 @@ __host__ __device__ inline float torch_linspace(float start, float end, int step
 __device__ inline float laplace_density(float s, float beta) {
   float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
   return (1.0f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(s) / beta));
+}
+
+// ---- NeRF++ background geometry (model/renderables/background.py), shared by background.cuh and the tcgen05 variant
+constexpr int kBgN = 32;        // N_samples_inverse_sphere
+constexpr int kBgEmbed = 84;    // 4 + 4*2*10
+constexpr int kBgFrame = 32;    // dim_frame_encoding
+constexpr int kBgView = 27;     // 3 + 3*2*4
+
+// inverse_sample (engine/ray_sampler.py:82-85) flipped (background.py:63-68): depth of sample k, 1 -> 0
+__device__ __forceinline__ float bg_depth(int k, float r_sphere) {
+  float t = torch_linspace(0.f, 1.f, kBgN, kBgN - 1 - k);
+  float z = 0.f * (1.0f - t) + 1.0f * t;
+  return z * (1.0f / r_sphere);
+}
+
+// Background.depth2pts_outside (background.py:102-135)
+__device__ __forceinline__ void depth2pts_outside(const float o[3], const float d[3], float depth, float R, float p4[4]) {
+  const float odd = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
+  const float under = odd * odd - ((o[0] * o[0] + o[1] * o[1] + o[2] * o[2]) - R * R);
+  const float ds = sqrtf(under) - odd;
+  float ps[3], pm[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { ps[c] = o[c] + ds * d[c]; pm[c] = o[c] - odd * d[c]; }
+  const float pmn = sqrtf(pm[0] * pm[0] + pm[1] * pm[1] + pm[2] * pm[2]);
+  float ax[3] = {o[1] * ps[2] - o[2] * ps[1], o[2] * ps[0] - o[0] * ps[2], o[0] * ps[1] - o[1] * ps[0]};
+  const float an = sqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) ax[c] = ax[c] / an;
+  const float phi = asinf(pmn / R), theta = asinf(pmn * depth);
+  const float ang = phi - theta, ca = cosf(ang), sa = sinf(ang);
+  const float cr[3] = {ax[1] * ps[2] - ax[2] * ps[1], ax[2] * ps[0] - ax[0] * ps[2], ax[0] * ps[1] - ax[1] * ps[0]};
+  const float dp = ax[0] * ps[0] + ax[1] * ps[1] + ax[2] * ps[2];
+  float pn[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pn[c] = ps[c] * ca + cr[c] * sa + ax[c] * dp * (1.0f - ca);
+  const float nn = sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);
+  p4[0] = pn[0] / nn, p4[1] = pn[1] / nn, p4[2] = pn[2] / nn, p4[3] = depth;
 }
 
 }  // namespace hold

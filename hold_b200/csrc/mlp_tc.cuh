@@ -89,6 +89,10 @@ struct TcArgs {
   int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too,
             // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel),
             // 32 = coarse hand-offs (pair kernel), 64 = LEAN reverse mode stashes t and computes softplus' in the backward rounds
+  const float* cam;          // background modes: ray origins / directions [R,3] of this frame chunk, its frame code [32]
+  const float* dirs;
+  const float* frame_code;
+  float r_sphere;
   long long* prof;  // pair kernel, HOLD_TC_PROF=1: cycle accounting of cluster 0 (see mlp_tc2.cuh)
 };
 
@@ -254,6 +258,27 @@ __device__ __noinline__ float embed_val(int e, int comp, float px, float py, flo
   return v;
 }
 
+// Background nets (HOLD_BG_TC=1): element e of the 84-wide embedding of the 4-d inverted-sphere point (10 frequencies) and of the
+// 27-wide embedding of the view direction (4 frequencies), engine/embedders.py:48-51 layout.  Not inlined (rolled call sites).
+__device__ __noinline__ float bg_embed_val(int e, float p0, float p1, float p2, float p3) {
+  if (e >= kBgEmbed) return 0.f;
+  const int d = (e < 4) ? e : ((e - 4) & 3);
+  const float pc = (d == 0) ? p0 : ((d == 1) ? p1 : ((d == 2) ? p2 : p3));
+  if (e < 4) return pc;
+  const int qq = (e - 4) >> 2;
+  const float arg = pc * (float)(1 << (qq >> 1));
+  return (qq & 1) ? cosf(arg) : sinf(arg);
+}
+__device__ __noinline__ float view_embed_val(int e, float d0, float d1, float d2) {
+  if (e >= kBgView) return 0.f;
+  const int d = e % 3;
+  const float pc = (d == 0) ? d0 : ((d == 1) ? d1 : d2);
+  if (e < 3) return pc;
+  const int qq = (e - 3) / 3;
+  const float arg = pc * (float)(1 << (qq >> 1));
+  return (qq & 1) ? cosf(arg) : sinf(arg);
+}
+
 constexpr int kTcW = 4;                        // epilogue warps per TMEM lane quarter
 constexpr int kTcChunk = 32;                   // accumulator columns per epilogue->MMA hand-off (= one weight stage of k)
 constexpr int kTcCW = kTcChunk / kTcW;         // accumulator columns per warp per chunk
@@ -279,9 +304,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 template <int MODE>
 struct TcCfg {
-  static constexpr int kAChunks = (MODE == MLP_COLOR) ? 5 : 4;   // 64-wide SW128 A chunks in smem
+  static constexpr bool kColorLike = (MODE == MLP_COLOR || MODE == MLP_BG_RGB);   // ReLU chain with a 3-row sigmoid head
+  static constexpr int kAChunks = kColorLike ? 5 : 4;   // 64-wide SW128 A chunks in smem
   static constexpr int kHandoffs = 2 * kAChunks;                 // 32-wide epilogue->MMA hand-offs
-  static constexpr int kStages = (MODE == MLP_COLOR) ? 2 : 3;
+  static constexpr int kStages = kColorLike ? 2 : 3;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
   static constexpr int kSmemW = kStages * kTcStageBytes;
   static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
@@ -292,6 +318,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   static_assert(!LEAN || MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV, "LEAN: SDF chains only");
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
+  constexpr bool kColorLike = Cfg::kColorLike;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
   constexpr int RPP = (MODE == MLP_SDF_JVP) ? 4 : 1;
   constexpr int PPT = kTcRows / RPP;
@@ -404,9 +431,37 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int p = tile * PPT + row / RPP;
       const bool valid = p < a.P;
-      float px = 0.f, py = 0.f, pz = 0.f;
+      float px = 0.f, py = 0.f, pz = 0.f, pw = 0.f;
       // ---------------------------------------------------------- prologue: layer-0 A operand (this warp's columns)
-      if (MODE != MLP_COLOR) {
+      if (MODE == MLP_BG_SDF) {
+        // inverted-sphere point of sample p % 32 of ray p / 32 (background.py:63-68,102-135), PE-10 + frame code: 116 -> 128
+        if (valid) {
+          const int ray = p / kBgN;
+          const float o[3] = {a.cam[3 * ray], a.cam[3 * ray + 1], a.cam[3 * ray + 2]};
+          const float d[3] = {a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2]};
+          float p4[4];
+          depth2pts_outside(o, d, bg_depth(p % kBgN, a.r_sphere), a.r_sphere, p4);
+          px = p4[0], py = p4[1], pz = p4[2], pw = p4[3];
+        }
+        const int b = valid ? p / a.pts_per_frame : 0;
+        for (int h = 0; h < 4; ++h) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = h * 32 + sub * 8 + i;
+            float v = 0.f;
+            if (e < kBgEmbed) v = bg_embed_val(e, px, py, pz, pw);
+            else if (e < kBgEmbed + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgEmbed];
+            x[i] = kTcScaleA * v;
+          }
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int c = h >> 1, j = (h & 1) * 4 + sub;
+          *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+          *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+          handoff_arrive(bAReady + 8 * h, lane);
+        }
+      } else if (!kColorLike) {
         if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
         for (int h = 0; h < 2; ++h) {
           float x[8];
@@ -436,9 +491,15 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]
+              const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]; background: [view PE-4 (27), frame code (32)]
               float v = 0.f;
-              if (valid) {
+              if (MODE == MLP_BG_RGB) {
+                if (valid) {
+                  const int ray = p / kBgN;
+                  if (e < kBgView) v = view_embed_val(e, a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2]);
+                  else if (e < kBgView + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgView];
+                }
+              } else if (valid) {
                 if (e < 3) v = a.xc[3 * (size_t)p + e];
                 else if (e < 6) v = a.normal[3 * (size_t)p + e - 3];
                 else if (e < 14) v = (a.pose_embed != nullptr) ? a.pose_embed[b * 8 + e - 6] : 0.f;
@@ -612,8 +673,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         continue;
       }
       for (int l = 0; l < a.n_layers; ++l) {
-        const bool feat_layer = (MODE == MLP_SDF_JVP) && (l == a.n_layers - 1);
-        const bool head_layer = (MODE == MLP_COLOR) ? (l == a.n_layers - 1) : (l == 7);
+        const bool feat_layer = (MODE == MLP_SDF_JVP || MODE == MLP_BG_SDF) && (l == a.n_layers - 1);
+        const bool head_layer = kColorLike ? (l == a.n_layers - 1) : (l == 7);
         const bool last_mma = (l == a.n_layers - 1);
         const int N = a.L[l].N;
         const float* bias = a.L[l].bias;
@@ -648,7 +709,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             // next layer's operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
             const float z = fmaf(acc[i], LEAN ? kLeanAccToT : kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
             float o;
-            if (MODE == MLP_COLOR) {
+            if (kColorLike) {
               o = fmaxf(z, 0.f) * kTcScaleA;
             } else if (feat_layer) {
               o = z;
@@ -667,17 +728,18 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             }
             out[i] = o;
           }
-          if (MODE != MLP_COLOR && n0 + 8 > N) {  // skip connection: embedding columns of layer 3's output
+          if (!kColorLike && n0 + 8 > N) {  // skip connection: embedding columns of layer 3's output
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (n0 + i >= N) out[i] = kTcScaleA * embed_val(n0 + i - N, comp, px, py, pz, a.embed_w);
+              if (n0 + i >= N)
+                out[i] = kTcScaleA * ((MODE == MLP_BG_SDF) ? bg_embed_val(n0 + i - N, px, py, pz, pw) : embed_val(n0 + i - N, comp, px, py, pz, a.embed_w));
           }
           if (head_layer) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
               head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
-              if (MODE == MLP_COLOR) {
+              if (kColorLike) {
                 const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + 256 + n0) + i);
                 const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.w_last + 512 + n0) + i);
                 head1 += out[4 * i] * w1.x + out[4 * i + 1] * w1.y + out[4 * i + 2] * w1.z + out[4 * i + 3] * w1.w;
@@ -704,9 +766,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       // ---------------------------------------------------------- heads: fixed-order reduction over the quarter's warps
       // (all MMAs of the tile have completed, so the A region is free to hold the partial sums)
       tc_fence_before();
-      constexpr int NH = (MODE == MLP_COLOR) ? 3 : 1;
+      constexpr int NH = kColorLike ? 3 : 1;
       scratch[(sub * NH + 0) * kTcRows + row] = head0;
-      if (MODE == MLP_COLOR) {
+      if (kColorLike) {
         scratch[(sub * NH + 1) * kTcRows + row] = head1;
         scratch[(sub * NH + 2) * kTcRows + row] = head2;
       }
@@ -720,7 +782,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           for (int w = 0; w < kTcW; ++w) acc += scratch[(w * NH + k) * kTcRows + row];
           h[k] = acc * (LEAN ? 1.0f : (1.0f / kTcScaleA));  // the head saw activations times kTcScaleA (LEAN: S, with pre-scaled head weights)
         }
-        if (MODE == MLP_COLOR) {
+        if (kColorLike) {
 #pragma unroll
           for (int k = 0; k < NH; ++k) a.rgb[3 * (size_t)p + k] = 1.0f / (1.0f + __expf(-(h[k] + a.b_last[k])));
         } else {
@@ -771,9 +833,10 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
   }
   for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
     int src = k;
-    if (perm_feat_first) {  // colour lin0: A order [feat(256) | x_c, n, pose(14) | time(32)] vs weight order [14 | 256 | 32]
-      if (k < kFeat) src = 14 + k;
-      else if (k < kFeat + 14) src = k - kFeat;
+    if (perm_feat_first) {  // colour lin0: A order [feat(256) | x_c, n, pose(14) | time(32)] vs weight order [14 | 256 | 32];
+      // background lin0: A order [feat(256) | view, frame (59)] vs weight order [59 | 256].  perm_feat_first = the leading width
+      if (k < kFeat) src = perm_feat_first + k;
+      else if (k < kFeat + perm_feat_first) src = k - kFeat;
       else src = k;
     }
     float w = (n < N && src < K) ? ((k < split) ? cs_lo : cs_hi) * (scale * (vr[src] * f)) : 0.f;
@@ -873,7 +936,7 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     const int K = (l == 0) ? rgb->in_dim[0] : 256, kpad = (l == 0) ? 320 : 256;
     t.rgb_nst[l] = kpad / 32;
     if (!t.rgb_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img[l], (size_t)t.rgb_nst[l] * kTcStageBytes));
-    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 1 : 0, kTcScaleW, kTcScaleW, 0,
+    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 14 : 0, kTcScaleW, kTcScaleW, 0,
                                   t.rgb_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }

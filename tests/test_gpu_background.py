@@ -73,3 +73,40 @@ def test_background_against_reference_golden(ctx):
     for k, v in out.items():
         err = (v.cpu() - ref[k]).abs().max().item()
         assert err <= 1e-5, f"{k}: {err:.2e}"
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
+def test_background_tcgen05_variant_matches_fp32(ctx):
+    """HOLD_BG_TC=1: the background nets on the tensor-core kernels against the exact-fp32 path (same inputs)."""
+    import os
+    import subprocess
+    import sys
+
+    code = """
+import torch, ctypes as C
+from hold_b200 import capi, scene_io, synth
+from hold_b200.capi import check, lib, ptr, stream_ptr
+ctx = capi.Context(0); dev = torch.device("cuda", 0)
+sc = synth.make_scene(H=10, W=10, S=32, B=2, seed=8)
+sc.intrinsics[:, 0, 2] += 0.37; sc.intrinsics[:, 1, 2] -= 0.21
+scene_io.build_net(sc, ctx, capi.MLP_FP32)
+bg, _, _ = scene_io.build_background(sc, ctx)
+from oracle import hold_oracle as O
+dirs, cam = O.camera_rays(sc.uv, sc.extrinsics, sc.intrinsics)
+P = dirs.shape[1]
+dirs, cam = dirs.reshape(-1, 3).to(dev), cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3).to(dev)
+out = bg(torch.rand(dirs.shape[0], generator=torch.Generator().manual_seed(0)).to(dev), dirs, cam, sc.frame_idx.to(dev), 2)
+ctx.check()
+torch.save({k: v.cpu() for k, v in out.items()}, OUT)
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for flag in ("0", "1"):
+        path = os.path.join(root, "tests", "_build", f"bg_tc_{flag}.pt")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        env = dict(os.environ, HOLD_BG_TC=flag, PYTHONPATH=root)
+        subprocess.run([sys.executable, "-c", code.replace("OUT", repr(path))], check=True, env=env, cwd=root, timeout=300)
+        res[flag] = torch.load(path)
+    for k in ("bg_rgb", "bg_rgb_only"):
+        err = (res["1"][k] - res["0"][k]).abs().max().item()
+        assert err < 2e-4, f"{k}: {err:.2e}"
