@@ -46,6 +46,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// the form CUTLASS' ClusterBarrier::arrive(cta_id) uses: default semantics (.release at CTA scope) on the remote barrier; the
+// data it publishes (this CTA's shared memory, read by the async proxy) has been ordered by fence.proxy.async before
+__device__ __forceinline__ void mbar_arrive_cluster_light(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -108,7 +113,7 @@ struct T2Epi {            // per-thread constants of an epilogue warp
   uint32_t d_full;        // local d_full[2][2]
   volatile int* abort_flag;
   int row, qh, sub, lane; // row 0..63 inside the CTA's half tile; qh = column half; sub = warp of the quarter
-  bool prof, coarse;
+  bool prof, coarse, light;
 };
 
 // `arrive`: fine-grained mode arrives after every round on a_ready[t][round]; coarse mode (HOLD_TC_DBG & 32) only after a
@@ -125,7 +130,10 @@ __device__ __forceinline__ void t2_store_a(const T2Epi& e, int t, int n0, int ro
   fence_proxy_async();
   tc_fence_before();
   __syncwarp();
-  if (e.lane == 0) mbar_arrive_cluster(e.a_ready + 8 * (t * 4 + round));
+  if (e.lane == 0) {
+    if (e.light) mbar_arrive_cluster_light(e.a_ready + 8 * (t * 4 + round));   // HOLD_TC_DBG & 128
+    else mbar_arrive_cluster(e.a_ready + 8 * (t * 4 + round));
+  }
 }
 
 // One (tile, step) of the epilogue.  KIND 0: forward layer l (softplus; REV: stash softplus'); 1: feature layer +
@@ -400,6 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     e.abort_flag = abort_flag;
     e.prof = prof;
     e.coarse = (a.dbg & 32) != 0;
+    e.light = (a.dbg & 128) != 0;
     const int w8 = e.qh * 4 + e.sub;  // index among the 8 warps that share this thread's row
     uint32_t d_par = 0;               // bit t*2+b = parity to wait for on d_full[t][b]
     for (int su = cluster_id; su < n_super; su += n_clusters) {
