@@ -13,7 +13,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first har
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_generate_grid_matches_reference_mise(ctx):
+def impl_generate_grid_matches_reference_mise(ctx):
     from hold_b200 import capi, meshing, scene_io, synth
 
     so = next(iter(glob.glob(os.path.join(ROOT, "oracle", "_ref", "mise*.so"))), None)
@@ -46,3 +46,7 @@ def test_generate_grid_matches_reference_mise(ctx):
     assert rounds >= 2 and grid.shape == ref.shape == (33, 33, 33)
     assert np.array_equal(grid, ref)
     assert (grid < 0).any() and (grid > 0).any()
+
+
+def test_generate_grid_matches_reference_mise(isolated):
+    isolated("tests/test_gpu_mise.py", "impl_generate_grid_matches_reference_mise")

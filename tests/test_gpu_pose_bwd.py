@@ -8,7 +8,7 @@ import torch
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
 
 
-def test_mano_server_backward(ctx):
+def impl_mano_server_backward(ctx):
     from hold_b200 import synth
     from hold_b200.model import MANOServer
     from oracle import hold_oracle as O
@@ -35,7 +35,7 @@ def test_mano_server_backward(ctx):
         assert err < 1e-4, f"{name}: {err:.2e}"
 
 
-def test_object_server_backward(ctx):
+def impl_object_server_backward(ctx):
     from hold_b200.model import ObjectServer
     from oracle import hold_oracle as O
 
@@ -58,3 +58,11 @@ def test_object_server_backward(ctx):
     for name, a, b in zip(("rot", "trans", "scene_scale", "obj_scale"), got, ref):
         err = (a.cpu() - b).abs().max().item() / max(1.0, b.abs().max().item())
         assert err < 1e-4, f"{name}: {err:.2e}"
+
+
+def test_mano_server_backward(isolated):
+    isolated("tests/test_gpu_pose_bwd.py", "impl_mano_server_backward")
+
+
+def test_object_server_backward(isolated):
+    isolated("tests/test_gpu_pose_bwd.py", "impl_object_server_backward")
