@@ -243,8 +243,8 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
 // Hand-node variant of k_inverse_warp<true, true> that walks `kSeg` consecutive samples of one ray per thread and
 // seeds each sample's KNN from the previous one (knn15_seeded).  Same arithmetic, same results.
 constexpr int kSeg = 32;
-__device__ __forceinline__ void
-inverse_warp_hand_rays_body(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
+__global__ void __launch_bounds__(128)
+k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
                          const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
                          const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
                          const SamplerState* __restrict__ st) {
@@ -283,18 +283,45 @@ inverse_warp_hand_rays_body(int rays_per_frame, int ns, int zstride, const float
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
-                         const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
-                         const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
-  inverse_warp_hand_rays_body(rays_per_frame, ns, zstride, zbuf, cam, dirs, tfs, verts, skin_w, xc, st);
-}
-// HOLD_KNN_OCC=1 (round-2 A/B): the same body compiled for >= 6 resident blocks per SM (<= 85 registers)
+// HOLD_KNN_OCC=1 (round-2 A/B): the same kernel text compiled for >= 6 resident blocks per SM (<= 85 registers)
 __global__ void __launch_bounds__(128, 6)
-k_inverse_warp_hand_rays_occ(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
-                             const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
-                             const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
-  inverse_warp_hand_rays_body(rays_per_frame, ns, zstride, zbuf, cam, dirs, tfs, verts, skin_w, xc, st);
+k_inverse_warp_hand_rays_occ(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
+                         const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
+                         const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
+                         const SamplerState* __restrict__ st) {
+  if (st != nullptr && st->done) return;
+  __shared__ float sv[kVerts * 3];
+  __shared__ float stf[kJoints * 16];
+  __shared__ unsigned short scand[128 * kKnnCand];
+  unsigned short* cand = scand + threadIdx.x * kKnnCand;
+  const int b = blockIdx.y;
+  for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
+  for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
+  __syncthreads();
+  const int segs = (ns + kSeg - 1) / kSeg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rays_per_frame * segs) return;
+  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
+  const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
+  const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
+  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+  Knn15 nn;
+  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
+  for (int k = k0; k < k1; ++k) {
+    const float tz = zbuf[ray * zstride + k];
+    const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
+    if (k == k0) knn15(sv, x, y, z, nn);
+    else knn15_seeded(sv, x, y, z, nn, cand);
+    float T[12], s, dmin;
+    blend_tf(nn, skin_w, stf, T, s, dmin);
+    float Ai[9];
+    inv3(T, 4, Ai);
+    const float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
+    const size_t gp = ray * ns + k;
+    xc[3 * gp] = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
+    xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
+    xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
+  }
 }
 
 // HOLD_KNN_FILTER=1 (round-2 A/B): the same walk with the filtered exact KNN of knn_phases.h (one 16-byte shared load + 3 FMA per
