@@ -16,6 +16,7 @@
 #include "pose_bwd.cuh"
 #include "mesh_sdf.cuh"
 #include "mise.cuh"
+#include "warp_bwd.cuh"
 
 namespace hold {
 
@@ -657,6 +658,35 @@ int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float thr
   if (R == 0) return HOLD_OK;
   HOLD_REQUIRE(sdf != nullptr, "NULL argument");
   k_off_in_surface<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(R, S, sdf, threshold, off_surface, in_surface);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_inverse_warp_bwd(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose, const int32_t* knn_idx,
+                          const float* g_xc, float* g_tfs, float* g_x, void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  HOLD_REQUIRE(B >= 0 && P >= 0, "bad sizes");
+  if (B == 0) return HOLD_OK;
+  HOLD_REQUIRE(pose && pose->tfs && g_tfs && (P == 0 || (x && g_xc)), "NULL argument");
+  NodeState& ns = ctx->nodes[node];
+  const bool hand = ns.cfg.kind == HOLD_KIND_HAND;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = max(1, ceil_div(P, 128));
+  void* part = nullptr;
+  if ((rc = ws_get(ctx, 22 /* WS_WARPBWD */, (size_t)B * nb * warpbwd::kJ * warpbwd::kG * sizeof(float), &part))) return rc;
+  dim3 grid(nb, B);
+  if (hand) {
+    HOLD_REQUIRE(ns.has_rig, "hand node has no rig (hold_node_set_rig)");
+    HOLD_REQUIRE(P == 0 || (knn_idx && pose->posed_verts), "hand backward needs the forward's knn_idx and the posed vertices");
+    k_inverse_warp_bwd_hand<<<grid, 128, 0, s>>>(P, x, knn_idx, pose->posed_verts, ns.skin_w, pose->tfs, g_xc, g_x, (float*)part);
+    HOLD_LAUNCH_CHECK(ctx);
+    k_inverse_warp_bwd_hand_final<<<B, 256, 0, s>>>(nb, (const float*)part, g_tfs);
+  } else {
+    k_inverse_warp_bwd_obj<<<grid, 128, 0, s>>>(P, x, pose->tfs, g_xc, g_x, (float*)part);
+    HOLD_LAUNCH_CHECK(ctx);
+    k_inverse_warp_bwd_obj_final<<<B, 16, 0, s>>>(nb, (const float*)part, g_tfs);
+  }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

@@ -73,6 +73,18 @@ def inverse_warp(node, x, pose: NodePose, want_idx=False):
     return xc, idx, mask
 
 
+def inverse_warp_bwd(node, x, pose: NodePose, knn_idx, g_xc, want_gx=False):
+    """Reverse mode of `inverse_warp` w.r.t. the transforms: g_xc [B,P,3] -> g_tfs ([B,16,4,4] hand / [B,4,4] object), g_x."""
+    B, P, _ = x.shape
+    hand = node.kind == "hand"
+    g_tfs = torch.empty((B, 16, 4, 4) if hand else (B, 4, 4), device=x.device)
+    g_x = torch.empty(B, P, 3, device=x.device) if want_gx else None
+    check(lib().hold_inverse_warp_bwd(node.ctx.h, node.slot, B, P, ptr(x.float().contiguous()), C.byref(pose),
+                                      ptr(knn_idx) if knn_idx is not None else None, ptr(g_xc.float().contiguous()), ptr(g_tfs), ptr(g_x),
+                                      stream_ptr()))
+    return g_tfs, g_x
+
+
 def compute_mano_cano_sdf(ctx, mesh_v_cano, mesh_f_cano, x_cano):
     """engine/volsdf_utils.py:172-186 without kaolin: signed distance [B,P] of x_cano [B,P,3] to the closed mesh
     (mesh_v_cano [B,V,3] or [V,3]; mesh_f_cano [F,3] integer)."""

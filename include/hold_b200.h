@@ -236,6 +236,13 @@ int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c /*[P,3]*/, co
 int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose,
                       float* x_c, int32_t* knn_idx, uint8_t* outlier_mask, void* stream);
 
+/* Reverse mode of hold_inverse_warp w.r.t. the transforms (skinning weights are detached in the reference, deformer.py:101):
+ * g_xc [B,P,3] -> g_tfs (hand [B,16,4,4], object [B,4,4]; the constant last row gets 0 except [3][3]) and, optionally, g_x
+ * [B,P,3].  Hand nodes need the forward's knn_idx [B,P,15].  With hold_sdf_eval's d sdf / d x_c upstream and
+ * hold_mano_lbs_bwd (g_tfs) downstream this is a joint SDF + LBS backward for pose refinement (BASELINE configs[4]). */
+int hold_inverse_warp_bwd(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose, const int32_t* knn_idx,
+                          const float* g_xc, float* g_tfs, float* g_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
