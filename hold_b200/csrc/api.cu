@@ -134,8 +134,9 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
     // hot path: consecutive samples of a ray per thread, KNN seeded from the previous sample
     const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
     dim3 g2(ceil_div(rays * segs, 128), B);
-    static const bool knn_occ = [] { const char* e = getenv("HOLD_KNN_OCC"); return e != nullptr && atoi(e) != 0; }();
-    static const bool knn_filt = [] { const char* e = getenv("HOLD_KNN_FILTER"); return e != nullptr && atoi(e) != 0; }();
+    // experiment switches, read per launch so that one process can A/B them (tools/exp_matrix.py)
+    const bool knn_occ = [] { const char* e = getenv("HOLD_KNN_OCC"); return e != nullptr && atoi(e) != 0; }();
+    const bool knn_filt = [] { const char* e = getenv("HOLD_KNN_FILTER"); return e != nullptr && atoi(e) != 0; }();
     if (knn_filt) k_inverse_warp_hand_rays_filt<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     else if (knn_occ) k_inverse_warp_hand_rays_occ<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     else k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);

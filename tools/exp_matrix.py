@@ -54,3 +54,37 @@ for name, env in VARIANTS:
         print(f"{name:28s} {t0:12.2f} {2 * 459008 * P / t0 / 1e9:8.1f} {t1 * (1 << 20) / Pg:10.2f} {e0:9.2e} {rel(grad[:Pr], ref[1]):9.2e} {rel(feat[:Pr], ref[2]):9.2e}", flush=True)
     except Exception as ex:
         print(f"{name:28s} FAILED: {ex}", flush=True)
+
+
+# ------------------------------------------------------------------ whole foreground step (all kernels), small frame
+STEP_VARIANTS = [
+    ("default", dict()),
+    ("KNN filtered scan", dict(HOLD_KNN_FILTER="1")),
+    ("KNN 6 blocks/SM", dict(HOLD_KNN_OCC="1")),
+    ("LEAN SDF kernels", dict(HOLD_TC_LEAN="1")),
+    ("LEAN + t-stash", dict(HOLD_TC_LEAN="1", HOLD_TC_DBG="64")),
+    ("LEAN + KNN filter", dict(HOLD_TC_LEAN="1", HOLD_KNN_FILTER="1")),
+]
+sc2 = synth.make_scene(H=192, W=192, S=128, nodes=("right", "object"), B=1, seed=0)
+for nid in sc2.node_ids:
+    sc2.beta[nid] = torch.tensor(0.03)
+net2 = scene_io.build_net(sc2, ctx, capi.MLP_TC)
+inp2 = scene_io.scene_input(sc2, dev)
+base = None
+print(f"\n{'foreground step 192x192':28s} {'ms':>9s} {'k rays/s':>9s} {'max|d fg_rgb| vs default':>26s}")
+for name, env in STEP_VARIANTS:
+    for k in ("HOLD_TC_PAIR", "HOLD_TC_LEAN", "HOLD_TC_DBG", "HOLD_KNN_FILTER", "HOLD_KNN_OCC"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    try:
+        out = {}
+        def step():
+            out["o"] = net2.forward_fg(inp2, return_factors=False)
+        t = timed(step, n=2)
+        ctx.check()
+        rgb = out["o"]["fg_rgb"].clone()
+        if base is None:
+            base = rgb
+        print(f"{name:28s} {t:9.1f} {192 * 192 / t:9.1f} {(rgb - base).abs().max().item():26.2e}", flush=True)
+    except Exception as ex:
+        print(f"{name:28s} FAILED: {ex}", flush=True)
