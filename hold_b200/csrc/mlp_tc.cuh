@@ -314,10 +314,27 @@ struct TcCfg {
   static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
-template <int MODE, bool LEAN = false>
+// PROF (HOLD_TC_PROF=1, sampler-round kernel only): CTA 0 accounts the cycles its role warps spend waiting, into a.prof:
+// [0] MMA warp total, [1] waiting for hand-offs, [2] waiting for weight stages; [8] producer total, [9] waiting for a free
+// stage; [16] epilogue warp 2 total, [17] waiting for the accumulator; [20], [21] the same for epilogue warp 17.
+template <bool PROF>
+__device__ __forceinline__ bool mbar_wait_p(uint32_t bar, uint32_t parity, int* err, int tag, volatile int* abort_flag, bool on,
+                                            long long& acc) {
+  if (!PROF || !on) return mbar_wait(bar, parity, err, tag, abort_flag);
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity, err, tag, abort_flag);
+  acc += clock64() - t0;
+  return ok;
+}
+
+template <int MODE, bool LEAN = false, bool PROF = false>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   static_assert(!LEAN || MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV, "LEAN: SDF chains only");
+  static_assert(!PROF || MODE == MLP_SDF_ONLY, "PROF: sampler-round kernel only");
   if (a.st != nullptr && a.st->done) return;
+  const bool prof_on = PROF && a.prof != nullptr && blockIdx.x == 0;
+  long long tp0 = 0, tp1 = 0;
+  const long long t_begin = prof_on ? clock64() : 0;
   using Cfg = TcCfg<MODE>;
   constexpr bool kColorLike = Cfg::kColorLike;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
@@ -359,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         for (int l = 0; l < a.n_layers; ++l) {
           const uint8_t* src = a.L[l].wimg;
           for (int s = 0; s < a.L[l].nst; ++s) {
-            if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag, prof_on, tp0))) goto tc_done;
             if (elect_one()) {
               if (a.dbg & 8) {
                 mbar_arrive(bWFull + 8 * stage);
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           }
         }
       }
+      if (PROF && prof_on && lane == 0) { a.prof[8] = clock64() - t_begin; a.prof[9] = tp0; }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer (whole warp walks the loop, one elected lane issues)
@@ -387,9 +405,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           for (int s = 0; s < nst; ++s) {
             const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
             // hand-off s = columns [32 s, 32 s + 32) of the previous layer's activations
-            if (!__all_sync(0xffffffffu, mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag, prof_on, tp0))) goto tc_done;
             a_par ^= (1u << s);
-            if (!__all_sync(0xffffffffu, mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bWFull + 8 * stage, phase, a.err, 3, abort_flag, prof_on, tp1))) goto tc_done;
             tc_fence_after();
             const uint32_t wb = sW + stage * kTcStageBytes;
             const bool el = elect_one();
@@ -414,6 +432,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           __syncwarp();
         }
       }
+      if (PROF && prof_on && lane == 0) { a.prof[0] = clock64() - t_begin; a.prof[1] = tp0; a.prof[2] = tp1; }
     }
   } else {
     // ============================================================ epilogue: kTcW warps per TMEM lane quarter; warp
@@ -681,7 +700,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         const float* bias = a.L[l].bias;
         float4 nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));      // issued before the wait
         float4 nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
-        if (!mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag)) break;
+        if (!mbar_wait_p<PROF>(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag, prof_on, tp0)) break;
         d_par ^= (1u << (l & 1));
         tc_fence_after();
         const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
@@ -793,6 +812,11 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       }
       epi_bar();  // scratch is overwritten by the next tile's prologue
     }
+    if (PROF && prof_on && lane == 0 && (warp == 2 || warp == 17)) {
+      const int o = (warp == 2) ? 16 : 20;
+      a.prof[o] = clock64() - t_begin;
+      a.prof[o + 1] = tp0;
+    }
   }
 tc_done:
   tc_fence_before();
@@ -881,6 +905,7 @@ static int tc_init(hold_ctx*) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_JVP>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
@@ -986,7 +1011,13 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
     k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
   } else {
     int tiles = ceil_div(P, kTcRows);
-    if (lean) k_mlp_tc<MLP_SDF_ONLY, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    if (!lean && getenv("HOLD_TC_PROF") != nullptr) {   // cycle accounting of CTA 0 (tools/prof_pair.py reads workspace slot 23)
+      void* pr = nullptr;
+      int rc = ws_get(ctx, 23 /* WS_PROF (debug) */, 64 * sizeof(long long), &pr);
+      if (rc) return rc;
+      a.prof = (long long*)pr;
+      k_mlp_tc<MLP_SDF_ONLY, false, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    } else if (lean) k_mlp_tc<MLP_SDF_ONLY, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
     else k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);

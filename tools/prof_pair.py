@@ -30,6 +30,13 @@ for tok in (sys.argv[1:] or ["1:0"]):
     except Exception as ex:
         print("check:", ex)
     line = f"pair={int(pair)} dbg={dbg:2d}: {ms:7.2f} ms  ({ms * 4:6.1f} ms at bench size)"
+    if not pair and os.environ.get("HOLD_TC_PROF"):
+        t = torch.zeros(64, dtype=torch.int64, device=dev)
+        assert L.hold_debug_ws_copy(ctx.h, 23, C.c_void_p(t.data_ptr()), C.c_size_t(64 * 8)) == 0
+        v = t.cpu().tolist()
+        tot = max(v[0], 1)
+        line += (f"\n    single-CTA kernel, CTA 0: mma warp waits hand-offs {v[1]/tot:.2f} weights {v[2]/tot:.2f};"
+                 f" producer waits free stage {v[9]/max(v[8],1):.2f}; epilogue waits accumulator w2 {v[17]/max(v[16],1):.2f} w17 {v[21]/max(v[20],1):.2f}")
     if pair and os.environ.get("HOLD_TC_PROF"):
         t = torch.zeros(64, dtype=torch.int64, device=dev)
         assert L.hold_debug_ws_copy(ctx.h, 23, C.c_void_p(t.data_ptr()), C.c_size_t(64 * 8)) == 0
