@@ -9,6 +9,7 @@
 #include "sampler.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_fast.cuh"
 #include "mlp_tc2.cuh"
 #include "composite.cuh"
 #include "background.cuh"
@@ -198,6 +199,7 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
   if (rc == HOLD_OK) rc = tc2_init();
+  if (rc == HOLD_OK) rc = tc_fast_init();
   if (rc == HOLD_OK) rc = tc_bg_init();
   if (rc) { delete ctx; return rc; }
   *out = ctx;
