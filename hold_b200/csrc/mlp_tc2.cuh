@@ -513,7 +513,10 @@ static int tc2_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, 
                           float* feat, const SamplerState* st, cudaStream_t s) {
   const bool rev = (grad != nullptr) || (feat != nullptr);
   static const bool use_jvp = [] { const char* e = getenv("HOLD_TC_GRAD"); return e != nullptr && strcmp(e, "jvp") == 0; }();
-  if (!rev && tc_fast_enabled()) return tc_fast_launch_sdf(ctx, ns, P, xc, embed_w, sdf, st, s);   // HOLD_TC_FAST=1 (sampler rounds)
+  if (tc_fast_enabled() && !(rev && use_jvp)) {   // HOLD_TC_FAST=1: rebuilt epilogue (mlp_tc_fast.cuh)
+    if (rev) return tc_fast_launch_rev(ctx, ns, P, xc, embed_w, sdf, grad, feat, s);
+    return tc_fast_launch_sdf(ctx, ns, P, xc, embed_w, sdf, st, s);
+  }
   if (!tc2_enabled() || (rev && use_jvp)) return tc_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
   TcArgs a;
   memset(&a, 0, sizeof(a));

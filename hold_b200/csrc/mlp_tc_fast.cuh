@@ -225,8 +225,274 @@ fast_done:
   }
 }
 
+// ------------------------------------------------------------------------------------------------ reverse mode (shading)
+// The 17-step chain of k_mlp_tc<MLP_SDF_REV> (8 forward layers stashing softplus', feature layer, 8 backward layers over the
+// transposed images) with the same rebuilt epilogue: 16 columns per warp and round, LEAN forward arithmetic, and the stash holds
+// t = 100 z log2(e) — softplus'(z) = sigmoid_t(t) is evaluated where it is consumed (backward rounds, whose MUFU pipe is idle)
+// instead of costing the forward rounds a third MUFU per element.
+// KIND 0: forward layer l; 1: feature layer + seed of the backward chain; 2: backward through layer l; 3: layer 0 (embedding).
+template <int KIND>
+__device__ __forceinline__ bool fast_rev_step(const TcArgs& a, int st, int l, uint32_t t_lane, uint32_t bDFull, uint32_t bAReady,
+                                              uint8_t* gA_hi, uint8_t* gA_lo, float* sig, int row, int sub, int lane, float px, float py,
+                                              float pz, bool valid, int p, uint32_t& d_par, volatile int* abort_flag, float& head0,
+                                              float& gx, float& gy, float& gz) {
+  constexpr int kSigL = kTcRows * 256;
+  const float* side = (KIND <= 1) ? a.L[st].bias : ((KIND == 2) ? sig + (size_t)(l - 1) * kSigL : nullptr);
+  if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) return false;
+  d_par ^= (1u << (st & 1));
+  tc_fence_after();
+  const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 16);
+  uint32_t raw[16];
+  tc_ld16(t_col, raw);
+#pragma unroll
+  for (int h = 0; h < kFastHandoffs; ++h) {
+    const int n0 = h * 64 + sub * 16;
+    float4 sv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sv[u] = (KIND == 3) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(side + n0 + 4 * u);
+    tc_wait_ld();
+    float out[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(raw[i]);
+    if (h + 1 < kFastHandoffs) tc_ld16(t_col + (uint32_t)((h + 1) * 64), raw);
+    if (KIND == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float e;
+        const float t0 = fmaf(out[4 * u + 0], kLeanAccToT, sv[u].x), t1 = fmaf(out[4 * u + 1], kLeanAccToT, sv[u].y);
+        const float t2 = fmaf(out[4 * u + 2], kLeanAccToT, sv[u].z), t3 = fmaf(out[4 * u + 3], kLeanAccToT, sv[u].w);
+        *reinterpret_cast<float4*>(sig + (size_t)l * kSigL + n0 + 4 * u) = make_float4(t0, t1, t2, t3);   // the stash holds t
+        out[4 * u + 0] = softplus_t(t0, e), out[4 * u + 1] = softplus_t(t1, e);
+        out[4 * u + 2] = softplus_t(t2, e), out[4 * u + 3] = softplus_t(t3, e);
+      }
+      if (l == 3 && n0 + 16 > kHidden - kEmbed) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + i >= kHidden - kEmbed) out[i] = kTcScaleA * embed_val(n0 + i - (kHidden - kEmbed), 0, px, py, pz, a.embed_w);
+      }
+      if (l == 7) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + u);
+          head0 += out[4 * u] * w.x + out[4 * u + 1] * w.y + out[4 * u + 2] * w.z + out[4 * u + 3] * w.w;
+        }
+      }
+    } else if (KIND == 1) {
+      constexpr float ks = kTcScaleA / kLeanAct;   // a.w_last holds w_sdf * ln2/100
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (valid)
+          *reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0 + 4 * u) =
+              make_float4(fmaf(out[4 * u], kLeanAccToZ, sv[u].x), fmaf(out[4 * u + 1], kLeanAccToZ, sv[u].y),
+                          fmaf(out[4 * u + 2], kLeanAccToZ, sv[u].z), fmaf(out[4 * u + 3], kLeanAccToZ, sv[u].w));
+        const float4 t7 = *reinterpret_cast<const float4*>(sig + (size_t)7 * kSigL + n0 + 4 * u);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + u);
+        out[4 * u + 0] = ks * w.x * sigmoid_t(t7.x), out[4 * u + 1] = ks * w.y * sigmoid_t(t7.y);
+        out[4 * u + 2] = ks * w.z * sigmoid_t(t7.z), out[4 * u + 3] = ks * w.w * sigmoid_t(t7.w);
+      }
+    } else if (KIND == 2) {
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = out[i] * kTcUnscale;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        out[4 * u + 0] = kTcScaleA * acc[4 * u + 0] * sigmoid_t(sv[u].x), out[4 * u + 1] = kTcScaleA * acc[4 * u + 1] * sigmoid_t(sv[u].y);
+        out[4 * u + 2] = kTcScaleA * acc[4 * u + 2] * sigmoid_t(sv[u].z), out[4 * u + 3] = kTcScaleA * acc[4 * u + 3] * sigmoid_t(sv[u].w);
+      }
+      if (l == 4 && n0 + 16 > kHidden - kEmbed) {   // skip input of layer 4: columns 217.. are d sdf / d embed
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (n0 + i >= kHidden - kEmbed) {
+            const int em = n0 + i - (kHidden - kEmbed), d = em % 3;
+            const float je = acc[i] * embed_val(em, d + 1, px, py, pz, a.embed_w);
+            gx += (d == 0) ? je : 0.f;
+            gy += (d == 1) ? je : 0.f;
+            gz += (d == 2) ? je : 0.f;
+            out[i] = 0.f;
+          }
+        }
+      }
+    } else {   // KIND 3: d sdf / d embed through layer 0's input (columns 0..38)
+      if (n0 < 48) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int em = n0 + i;
+          if (em < kEmbed) {
+            const int d = em % 3;
+            const float je = out[i] * kTcUnscale * embed_val(em, d + 1, px, py, pz, a.embed_w);
+            gx += (d == 0) ? je : 0.f;
+            gy += (d == 1) ? je : 0.f;
+            gz += (d == 2) ? je : 0.f;
+          }
+        }
+      }
+    }
+    if (KIND != 3) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint4 hi, lo;
+        split8(out + 8 * u, hi, lo);
+        const uint32_t off = (uint32_t)(h * kTcAChunkBytes) + a_unit_off(row, sub * 2 + u);
+        *reinterpret_cast<uint4*>(gA_hi + off) = hi;
+        *reinterpret_cast<uint4*>(gA_lo + off) = lo;
+      }
+      handoff_arrive(bAReady + 8 * h, lane);
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc_fast_rev(TcArgs a) {
+  constexpr int NS = kFastStages, NHO = kFastHandoffs;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA_hi = base, sA_lo = base + 4 * kTcAChunkBytes, sW = base + kFastSmemA;
+  const uint32_t sBar = sW + NS * kTcStageBytes;
+  const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NHO;
+  const uint32_t sTmemPtr = bDFull + 16, sAbort = bDFull + 20;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(gen_base + (sAbort - base));
+  const int n_tiles = ceil_div(a.P, kTcRows);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
+    *abort_flag = 0;
+    for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, kTcEpiWarps);
+    mbar_init(bDFull, 1);
+    mbar_init(bDFull + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int st = 0; st < 17; ++st) {
+        const uint8_t* src = a.L[st].wimg;
+        for (int s = 0; s < a.L[st].nst; ++s) {
+          if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto fastrev_done;
+          if (elect_one()) {
+            mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
+            bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
+          }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int st = 0; st < 17; ++st) {
+        const uint32_t d_tmem = tmem_u + (uint32_t)((st & 1) * 256);
+        const int nst = a.L[st].nst;
+        for (int s = 0; s < nst; ++s) {
+          const int c = s >> 1;
+          if ((s & 1) == 0) {
+            if (!__all_sync(0xffffffffu, mbar_wait(bAReady + 8 * c, (a_par >> c) & 1, a.err, 2, abort_flag))) goto fastrev_done;
+            a_par ^= (1u << c);
+          }
+          if (!__all_sync(0xffffffffu, mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag))) goto fastrev_done;
+          tc_fence_after();
+          const uint32_t wb = sW + stage * kTcStageBytes;
+          const bool el = elect_one();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);
+            const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+            const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+            const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
+            const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
+            if (el) {
+              tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
+              tc_mma(d_tmem, alo, whi, kIdescF16, 1);
+              tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
+            }
+          }
+          if (el) tc_commit(bWEmpty + 8 * stage);
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) tc_commit(bDFull + 8 * (st & 1));
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3, sub = (warp - 2) >> 2, row = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* gA_hi = gen_base;
+    uint8_t* gA_lo = gen_base + 4 * kTcAChunkBytes;
+    float* scratch = reinterpret_cast<float*>(gen_base);
+    float* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
+    uint32_t d_par = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int p = tile * kTcRows + row;
+      const bool valid = p < a.P;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
+      {
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = kTcScaleA * embed_val(sub * 16 + i, 0, px, py, pz, a.embed_w);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint4 hi, lo;
+          split8(x + 8 * u, hi, lo);
+          *reinterpret_cast<uint4*>(gA_hi + a_unit_off(row, sub * 2 + u)) = hi;
+          *reinterpret_cast<uint4*>(gA_lo + a_unit_off(row, sub * 2 + u)) = lo;
+        }
+        handoff_arrive(bAReady, lane);
+      }
+      float head0 = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+      bool ok = true;
+#define FAST_REV(KIND, ST, L) fast_rev_step<KIND>(a, ST, L, t_lane, bDFull, bAReady, gA_hi, gA_lo, sig, row, sub, lane, px, py, pz, valid, p, d_par, abort_flag, head0, gx, gy, gz)
+      for (int st = 0; st < 8 && ok; ++st) ok = FAST_REV(0, st, st);
+      if (ok) ok = FAST_REV(1, 8, 8);
+      for (int st = 9; st < 16 && ok; ++st) ok = FAST_REV(2, st, 16 - st);
+      if (ok) ok = FAST_REV(3, 16, 0);
+#undef FAST_REV
+      tc_fence_before();
+      scratch[(sub * 4 + 0) * kTcRows + row] = head0;
+      scratch[(sub * 4 + 1) * kTcRows + row] = gx;
+      scratch[(sub * 4 + 2) * kTcRows + row] = gy;
+      scratch[(sub * 4 + 3) * kTcRows + row] = gz;
+      epi_bar();
+      if (sub == 0 && valid) {
+        float hs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w = 0; w < kTcW; ++w) acc += scratch[(w * 4 + k) * kTcRows + row];
+          hs[k] = acc;
+        }
+        a.sdf[p] = hs[0] + a.b_last[0];
+        a.grad[3 * (size_t)p] = hs[1], a.grad[3 * (size_t)p + 1] = hs[2], a.grad[3 * (size_t)p + 2] = hs[3];
+      }
+      epi_bar();
+    }
+  }
+fastrev_done:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 static int tc_fast_init() {
   cudaError_t e = cudaFuncSetAttribute(k_mlp_tc_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc_fast_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 fast kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
   return HOLD_OK;
 }
@@ -249,6 +515,32 @@ static int tc_fast_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* 
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.st = st, a.err = ctx->dev_err;
   const int tiles = ceil_div(P, kTcRows);
   k_mlp_tc_fast<<<min(tiles, ctx->sm_count), kTcThreadsTotal, kFastSmemBytes, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+// shading launch: sdf + gradient + feature (reverse mode), LEAN forward images and the transposed images for the backward half
+static int tc_fast_launch_rev(hold_ctx* ctx, NodeState& ns, int P, const float* xc, const float* embed_w, float* sdf, float* grad,
+                              float* feat, cudaStream_t s) {
+  HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = P, a.n_layers = 17;
+  for (int l = 0; l < 9; ++l) {
+    a.L[l].wimg = ns.tc->sdf_imgL[l], a.L[l].bias = (l < 8) ? ns.tc->sdf_bias_t[l] : ns.sdf.bias[8], a.L[l].nst = ns.tc->sdf_nst[l];
+    a.L[l].N = ns.sdf.N[l];
+  }
+  for (int i = 0; i < 8; ++i) {
+    a.L[9 + i].wimg = ns.tc->sdf_imgT[7 - i], a.L[9 + i].bias = nullptr, a.L[9 + i].nst = 8, a.L[9 + i].N = 256;
+  }
+  a.w_last = ns.tc->w_last_t, a.b_last = ns.sdf.b_last;
+  a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.err = ctx->dev_err;
+  const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
+  void* sig = nullptr;
+  int rc = ws_get(ctx, 12 /* WS_SIG */, (size_t)grid * 8 * kTcRows * 256 * sizeof(float), &sig);
+  if (rc) return rc;
+  a.sig = (float*)sig;
+  k_mlp_tc_fast_rev<<<grid, kTcThreadsTotal, kFastSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

@@ -11,7 +11,7 @@ VARIANTS = [
     ("single-CTA (default)", dict()),
     ("single-CTA LEAN", dict(HOLD_TC_LEAN="1")),
     ("single-CTA LEAN, t-stash", dict(HOLD_TC_LEAN="1", HOLD_TC_DBG="64")),
-    ("single-CTA FAST (sdf-only)", dict(HOLD_TC_FAST="1")),
+    ("single-CTA FAST", dict(HOLD_TC_FAST="1")),
     ("pair fine hand-offs", dict(HOLD_TC_PAIR="1")),
     ("pair coarse hand-offs", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="32")),
     ("pair fine, light arrive", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="128")),
@@ -65,7 +65,7 @@ STEP_VARIANTS = [
     ("LEAN SDF kernels", dict(HOLD_TC_LEAN="1")),
     ("LEAN + t-stash", dict(HOLD_TC_LEAN="1", HOLD_TC_DBG="64")),
     ("LEAN + KNN filter", dict(HOLD_TC_LEAN="1", HOLD_KNN_FILTER="1")),
-    ("FAST rounds + LEAN shading + KNN filter", dict(HOLD_TC_FAST="1", HOLD_TC_LEAN="1", HOLD_KNN_FILTER="1")),
+    ("FAST + KNN filter", dict(HOLD_TC_FAST="1", HOLD_KNN_FILTER="1")),
 ]
 sc2 = synth.make_scene(H=192, W=192, S=128, nodes=("right", "object"), B=1, seed=0)
 for nid in sc2.node_ids:
