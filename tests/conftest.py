@@ -43,7 +43,7 @@ def isolated(built):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
 
-    def run(module_path, func, timeout=420, env=None):
+    def run(module_path, func, timeout=240, env=None):
         code = (
             "import sys, importlib.util, torch\n"
             f"sys.path.insert(0, {ROOT!r})\n"
