@@ -62,6 +62,9 @@ struct TcMlp {
   uint8_t* sdf_imgL[HOLD_MAX_LAYERS] = {nullptr};  // LEAN images of layers 0..8 (per-column operand scales)
   float* sdf_bias_t[8] = {nullptr};                 // LEAN: bias * 100 log2(e), layers 0..7
   float* w_last_t = nullptr;                        // LEAN: sdf head row * ln2/100
+  uint8_t* sdf_imgL_rep[HOLD_MAX_LAYERS] = {nullptr};   // HOLD_TC_WCOPIES: [copies][nst * 32 KB] replicas of sdf_imgL / sdf_imgT
+  uint8_t* sdf_imgT_rep[HOLD_MAX_LAYERS] = {nullptr};
+  int rep_copies = 0;
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient
@@ -94,6 +97,7 @@ struct TcArgs {
   const float* dirs;
   const float* frame_code;
   float r_sphere;
+  int wcopies;               // FAST kernels, HOLD_TC_WCOPIES=N: CTA b streams weight-image copy b % N (spreads the L2 hot lines)
   long long* prof;  // pair kernel, HOLD_TC_PROF=1: cycle accounting of cluster 0 (see mlp_tc2.cuh)
 };
 
@@ -919,6 +923,8 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
     if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
     if (ns.tc->sdf_imgL[l]) cudaFree(ns.tc->sdf_imgL[l]);
+    if (ns.tc->sdf_imgL_rep[l]) cudaFree(ns.tc->sdf_imgL_rep[l]);
+    if (ns.tc->sdf_imgT_rep[l]) cudaFree(ns.tc->sdf_imgT_rep[l]);
     if (l < 8 && ns.tc->sdf_bias_t[l]) cudaFree(ns.tc->sdf_bias_t[l]);
   }
   if (ns.tc->w_last_t) cudaFree(ns.tc->w_last_t);

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc_fast(TcArgs a) {
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int l = 0; l < 8; ++l) {
-        const uint8_t* src = a.L[l].wimg;
+        const uint8_t* src = a.L[l].wimg + (a.wcopies > 1 ? (size_t)(blockIdx.x % a.wcopies) * a.L[l].nst * kTcStageBytes : 0);
         for (int s = 0; s < a.L[l].nst; ++s) {
           if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto fast_done;
           if (elect_one()) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc_fast_rev(TcArgs a
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int st = 0; st < 17; ++st) {
-        const uint8_t* src = a.L[st].wimg;
+        const uint8_t* src = a.L[st].wimg + (a.wcopies > 1 ? (size_t)(blockIdx.x % a.wcopies) * a.L[st].nst * kTcStageBytes : 0);
         for (int s = 0; s < a.L[st].nst; ++s) {
           if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto fastrev_done;
           if (elect_one()) {
@@ -497,6 +497,30 @@ static int tc_fast_init() {
   return HOLD_OK;
 }
 
+// HOLD_TC_WCOPIES=N: N replicas of every weight image the FAST kernels stream, CTA b reads replica b % N — a test of (and remedy
+// for) L2 hot-spotting when 148 CTAs in near lock-step fetch the same 32 KB stage.  Built lazily, rebuilt when weights change.
+static int tc_fast_replicas(hold_ctx* ctx, NodeState& ns, cudaStream_t s) {
+  const char* e = getenv("HOLD_TC_WCOPIES");
+  const int n = e ? atoi(e) : 0;
+  if (n <= 1) return 0;
+  TcMlp& t = *ns.tc;
+  for (int l = 0; l < 9; ++l) {
+    const size_t bytes = (size_t)t.sdf_nst[l] * kTcStageBytes;
+    if (t.rep_copies != n && t.sdf_imgL_rep[l]) { cudaFree(t.sdf_imgL_rep[l]); t.sdf_imgL_rep[l] = nullptr; }
+    if (!t.sdf_imgL_rep[l] && cudaMalloc((void**)&t.sdf_imgL_rep[l], bytes * n) != cudaSuccess) return -1;
+    for (int c = 0; c < n; ++c) cudaMemcpyAsync(t.sdf_imgL_rep[l] + bytes * c, t.sdf_imgL[l], bytes, cudaMemcpyDeviceToDevice, s);
+  }
+  for (int l = 0; l < 8; ++l) {
+    const size_t bytes = (size_t)8 * kTcStageBytes;
+    if (t.rep_copies != n && t.sdf_imgT_rep[l]) { cudaFree(t.sdf_imgT_rep[l]); t.sdf_imgT_rep[l] = nullptr; }
+    if (!t.sdf_imgT_rep[l] && cudaMalloc((void**)&t.sdf_imgT_rep[l], bytes * n) != cudaSuccess) return -1;
+    for (int c = 0; c < n; ++c) cudaMemcpyAsync(t.sdf_imgT_rep[l] + bytes * c, t.sdf_imgT[l], bytes, cudaMemcpyDeviceToDevice, s);
+  }
+  t.rep_copies = n;
+  (void)ctx;
+  return n;
+}
+
 static inline bool tc_fast_enabled() {
   const char* e = getenv("HOLD_TC_FAST");
   return e != nullptr && atoi(e) != 0;
@@ -513,6 +537,12 @@ static int tc_fast_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* 
   }
   a.w_last = ns.tc->w_last_t, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.st = st, a.err = ctx->dev_err;
+  const int nrep = tc_fast_replicas(ctx, ns, s);   // refreshed per launch (a few MB of D2D copies; experiment only)
+  HOLD_REQUIRE(nrep >= 0, "out of memory for weight-image replicas");
+  if (nrep > 1) {
+    a.wcopies = nrep;
+    for (int l = 0; l < 8; ++l) a.L[l].wimg = ns.tc->sdf_imgL_rep[l];
+  }
   const int tiles = ceil_div(P, kTcRows);
   k_mlp_tc_fast<<<min(tiles, ctx->sm_count), kTcThreadsTotal, kFastSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
@@ -540,6 +570,13 @@ static int tc_fast_launch_rev(hold_ctx* ctx, NodeState& ns, int P, const float* 
   int rc = ws_get(ctx, 12 /* WS_SIG */, (size_t)grid * 8 * kTcRows * 256 * sizeof(float), &sig);
   if (rc) return rc;
   a.sig = (float*)sig;
+  const int nrep = tc_fast_replicas(ctx, ns, s);
+  HOLD_REQUIRE(nrep >= 0, "out of memory for weight-image replicas");
+  if (nrep > 1) {
+    a.wcopies = nrep;
+    for (int l = 0; l < 9; ++l) a.L[l].wimg = ns.tc->sdf_imgL_rep[l];
+    for (int i = 0; i < 8; ++i) a.L[9 + i].wimg = ns.tc->sdf_imgT_rep[7 - i];
+  }
   k_mlp_tc_fast_rev<<<grid, kTcThreadsTotal, kFastSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;

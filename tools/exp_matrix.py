@@ -12,6 +12,7 @@ VARIANTS = [
     ("single-CTA LEAN", dict(HOLD_TC_LEAN="1")),
     ("single-CTA LEAN, t-stash", dict(HOLD_TC_LEAN="1", HOLD_TC_DBG="64")),
     ("single-CTA FAST", dict(HOLD_TC_FAST="1")),
+    ("single-CTA FAST, 8 weight replicas", dict(HOLD_TC_FAST="1", HOLD_TC_WCOPIES="8")),
     ("pair fine hand-offs", dict(HOLD_TC_PAIR="1")),
     ("pair coarse hand-offs", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="32")),
     ("pair fine, light arrive", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="128")),
@@ -43,7 +44,7 @@ def timed(fn, n=3):
 rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1.0)).item()
 print(f"{'variant':28s} {'sdf-only ms':>12s} {'TFLOP/s':>8s} {'rev ms/Mi':>10s} {'e_sdf':>9s} {'e_grad':>9s} {'e_feat':>9s}")
 for name, env in VARIANTS:
-    for k in ("HOLD_TC_PAIR", "HOLD_TC_LEAN", "HOLD_TC_DBG", "HOLD_TC_FAST"):
+    for k in ("HOLD_TC_PAIR", "HOLD_TC_LEAN", "HOLD_TC_DBG", "HOLD_TC_FAST", "HOLD_TC_WCOPIES"):
         os.environ.pop(k, None)
     os.environ.update(env)
     try:
@@ -75,7 +76,7 @@ inp2 = scene_io.scene_input(sc2, dev)
 base = None
 print(f"\n{'foreground step 192x192':28s} {'ms':>9s} {'k rays/s':>9s} {'max|d fg_rgb| vs default':>26s}")
 for name, env in STEP_VARIANTS:
-    for k in ("HOLD_TC_PAIR", "HOLD_TC_LEAN", "HOLD_TC_DBG", "HOLD_TC_FAST", "HOLD_KNN_FILTER", "HOLD_KNN_OCC"):
+    for k in ("HOLD_TC_PAIR", "HOLD_TC_LEAN", "HOLD_TC_DBG", "HOLD_TC_FAST", "HOLD_TC_WCOPIES", "HOLD_KNN_FILTER", "HOLD_KNN_OCC"):
         os.environ.pop(k, None)
     os.environ.update(env)
     try:
