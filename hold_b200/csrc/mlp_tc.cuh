@@ -64,6 +64,7 @@ struct TcMlp {
   float* w_last_t = nullptr;                        // LEAN: sdf head row * ln2/100
   uint8_t* sdf_imgL_rep[HOLD_MAX_LAYERS] = {nullptr};   // HOLD_TC_WCOPIES: [copies][nst * 32 KB] replicas of sdf_imgL / sdf_imgT
   uint8_t* sdf_imgT_rep[HOLD_MAX_LAYERS] = {nullptr};
+  uint8_t* sdf_img_rep[HOLD_MAX_LAYERS] = {nullptr};    // replicas of the plain images (pair kernel)
   int rep_copies = 0;
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
@@ -925,6 +926,7 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->sdf_imgL[l]) cudaFree(ns.tc->sdf_imgL[l]);
     if (ns.tc->sdf_imgL_rep[l]) cudaFree(ns.tc->sdf_imgL_rep[l]);
     if (ns.tc->sdf_imgT_rep[l]) cudaFree(ns.tc->sdf_imgT_rep[l]);
+    if (ns.tc->sdf_img_rep[l]) cudaFree(ns.tc->sdf_img_rep[l]);
     if (l < 8 && ns.tc->sdf_bias_t[l]) cudaFree(ns.tc->sdf_bias_t[l]);
   }
   if (ns.tc->w_last_t) cudaFree(ns.tc->w_last_t);

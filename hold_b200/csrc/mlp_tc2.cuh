@@ -311,7 +311,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
       uint32_t stage = 0, phase = 0;
       for (int su = cluster_id; su < n_super; su += n_clusters) {
         for (int step = 0; step < NSTEP; ++step) {
-          const uint8_t* src = a.L[step].wimg + (size_t)rank * 8192;
+          const uint8_t* src = a.L[step].wimg + (size_t)rank * 8192 +
+                               (a.wcopies > 1 ? (size_t)(cluster_id % a.wcopies) * a.L[step].nst * kTcStageBytes : 0);
           const int nst = a.L[step].nst;
           for (int t = 0; t < 2; ++t) {
             for (int si = 0; si < nst; ++si) {
@@ -537,6 +538,15 @@ static int tc2_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, 
     a.prof = (long long*)pr;
   }
   const int grid = tc2_grid(ctx, P);
+  {
+    const int nrep = tc_fast_replicas(ctx, ns, s);   // HOLD_TC_WCOPIES=N: cluster c streams replica c % N
+    HOLD_REQUIRE(nrep >= 0, "out of memory for weight-image replicas");
+    if (nrep > 1) {
+      a.wcopies = nrep;
+      for (int l = 0; l < 9; ++l) a.L[l].wimg = ns.tc->sdf_img_rep[l];
+      for (int i = 0; i < 8; ++i) a.L[9 + i].wimg = ns.tc->sdf_imgT_rep[7 - i];
+    }
+  }
   if (rev) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     void* sig = nullptr;

@@ -509,6 +509,9 @@ static int tc_fast_replicas(hold_ctx* ctx, NodeState& ns, cudaStream_t s) {
     if (t.rep_copies != n && t.sdf_imgL_rep[l]) { cudaFree(t.sdf_imgL_rep[l]); t.sdf_imgL_rep[l] = nullptr; }
     if (!t.sdf_imgL_rep[l] && cudaMalloc((void**)&t.sdf_imgL_rep[l], bytes * n) != cudaSuccess) return -1;
     for (int c = 0; c < n; ++c) cudaMemcpyAsync(t.sdf_imgL_rep[l] + bytes * c, t.sdf_imgL[l], bytes, cudaMemcpyDeviceToDevice, s);
+    if (t.rep_copies != n && t.sdf_img_rep[l]) { cudaFree(t.sdf_img_rep[l]); t.sdf_img_rep[l] = nullptr; }
+    if (!t.sdf_img_rep[l] && cudaMalloc((void**)&t.sdf_img_rep[l], bytes * n) != cudaSuccess) return -1;
+    for (int c = 0; c < n; ++c) cudaMemcpyAsync(t.sdf_img_rep[l] + bytes * c, t.sdf_img[l], bytes, cudaMemcpyDeviceToDevice, s);
   }
   for (int l = 0; l < 8; ++l) {
     const size_t bytes = (size_t)8 * kTcStageBytes;
