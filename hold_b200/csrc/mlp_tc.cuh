@@ -93,7 +93,8 @@ struct TcArgs {
   int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too,
             // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel),
             // 32 = coarse hand-offs (pair kernel), 64 = LEAN reverse mode stashes t and computes softplus' in the backward rounds,
-            // 128 = pair kernel: hand-off arrivals with CTA-scope release (CUTLASS ClusterBarrier form) instead of release.cluster
+            // 128 = pair kernel: hand-off arrivals with CTA-scope release (CUTLASS ClusterBarrier form) instead of release.cluster,
+            // 256 = pair kernel, sampler rounds: FAST-shaped epilogue (2 rounds of 16 columns, coarse hand-offs)
   const float* cam;          // background modes: ray origins / directions [R,3] of this frame chunk, its frame code [32]
   const float* dirs;
   const float* frame_code;

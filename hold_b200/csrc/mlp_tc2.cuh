@@ -256,6 +256,75 @@ __device__ __forceinline__ bool t2_epi(const TcArgs& a, const T2Epi& e, int t, i
   return true;
 }
 
+// SDF-only forward step with the FAST epilogue shape (HOLD_TC_DBG & 256; implies coarse hand-offs): 2 rounds of 16 columns per
+// warp and tile-step, one fence + one arrival at the end, no experiment branches in the element loop.
+__device__ __forceinline__ bool t2_epi_wide0(const TcArgs& a, const T2Epi& e, int t, int step, bool store_a, float px, float py, float pz,
+                                             float& h0, uint32_t& d_par, long long& t_wait) {
+  const int l = step;
+  const int di = t * 2 + (step & 1);
+  if (!mbar_wait2t(e.d_full + 8 * di, (d_par >> di) & 1, a.err, 4, e.abort_flag, e.prof, t_wait)) return false;
+  d_par ^= (1u << di);
+  tc_fence_after();
+  const uint32_t t_col = e.t_lane + (uint32_t)(di * 128 + e.sub * 16);
+  uint32_t raw[16];
+  tc_ld16(t_col, raw);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int n0 = e.qh * 128 + j * 64 + e.sub * 16;
+    float4 b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const float4*>(e.bias + l * 256 + n0 + 4 * u);
+    tc_wait_ld();
+    float out[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(raw[i]);
+    if (j == 0) tc_ld16(t_col + 64u, raw);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float bb[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float z64 = fmaf(out[4 * u + i], kT2AccToZ64, bb[i]);
+        const float uu = mufu_ex2(-fabsf(z64 * kT2Z64ToT));
+        out[4 * u + i] = fmaf(mufu_lg2(1.0f + uu), kT2LgToOut, fmaxf(z64, 0.f));
+      }
+    }
+    if (l == 3 && n0 + 16 > kHidden - kEmbed) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + i >= kHidden - kEmbed) out[i] = kTcScaleA * embed_val(n0 + i - (kHidden - kEmbed), 0, px, py, pz, a.embed_w);
+    }
+    if (l == 7) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + u);
+        h0 += out[4 * u] * w.x + out[4 * u + 1] * w.y + out[4 * u + 2] * w.z + out[4 * u + 3] * w.w;
+      }
+    }
+    if (store_a) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint4 hi, lo;
+        split8(out + 8 * u, hi, lo);
+        const int k = n0 + 8 * u, c64 = k >> 6, ju = (k & 63) >> 3;
+        const uint32_t off = (uint32_t)(t * kT2ATile + c64 * 8192 + (e.row >> 3) * 1024 + (e.row & 7) * 128 + ((ju ^ (e.row & 7)) << 4));
+        *reinterpret_cast<uint4*>(e.gA + off) = hi;
+        *reinterpret_cast<uint4*>(e.gA + off + kT2APart) = lo;
+      }
+    }
+  }
+  if (store_a) {   // one arrival per warp and tile-step on a_ready[t][0]
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (e.lane == 0) {
+      if (e.light) mbar_arrive_cluster_light(e.a_ready + 8 * (t * 4));
+      else mbar_arrive_cluster(e.a_ready + 8 * (t * 4));
+    }
+  }
+  return true;
+}
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc2(TcArgs a) {
   static_assert(MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV, "pair kernel: SDF chains only");
@@ -362,7 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
             const uint32_t aT = sA + t * kT2ATile;
             for (int si = 0; si < nst; ++si) {
               const int c = (nst == 8) ? ((si >> 1) + 4 * (si & 1)) : si;
-              if ((si & 1) == 0 && (si == 0 || !(a.dbg & 32))) {  // one hand-off barrier per epilogue round: chunks j and 4 + j
+              if ((si & 1) == 0 && (si == 0 || !(a.dbg & (32 | 256)))) {  // one hand-off barrier per epilogue round: chunks j and 4 + j
                 // (layer 0: chunks 0, 1; coarse mode: one barrier per tile-step)
                 const int bi = t * 4 + (si >> 1);
                 if (!__all_sync(0xffffffffu, mbar_wait2t(bAReady + 8 * bi, (a_par >> bi) & 1, a.err, 2, abort_flag, prof, tp1))) goto tc2_done;
@@ -409,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
     e.d_full = bDFull;
     e.abort_flag = abort_flag;
     e.prof = prof;
-    e.coarse = (a.dbg & 32) != 0;
+    e.coarse = (a.dbg & (32 | 256)) != 0;
     e.light = (a.dbg & 128) != 0;
     const int w8 = e.qh * 4 + e.sub;  // index among the 8 warps that share this thread's row
     uint32_t d_par = 0;               // bit t*2+b = parity to wait for on d_full[t][b]
@@ -436,7 +505,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreadsTotal, 1) 
                             h3, d_par, tp0);                                                                                       \
     if (t) { hb0 = h0, hb1 = h1, hb2 = h2, hb3 = h3; } else { ha0 = h0, ha1 = h1, ha2 = h2, ha3 = h3; }                            \
   }
-      for (int l = 0; l < 8 && ok; ++l) { T2_STEP(0, l, l, (MODE == MLP_SDF_REV) || l < 7) }
+      if (MODE == MLP_SDF_ONLY && (a.dbg & 256)) {
+        for (int l = 0; l < 8 && ok; ++l)
+          for (int t = 0; t < 2 && ok; ++t) {
+            float h0 = t ? hb0 : ha0;
+            ok = t2_epi_wide0(a, e, t, l, l < 7, t ? x1 : x0, t ? y1 : y0, t ? z1 : z0, h0, d_par, tp0);
+            if (t) hb0 = h0; else ha0 = h0;
+          }
+      } else {
+        for (int l = 0; l < 8 && ok; ++l) { T2_STEP(0, l, l, (MODE == MLP_SDF_REV) || l < 7) }
+      }
       if (MODE == MLP_SDF_REV) {
         if (ok) { T2_STEP(1, 8, 8, true) }
         for (int step = 9; step < 16 && ok; ++step) { T2_STEP(2, step, 16 - step, true) }

@@ -18,6 +18,8 @@ VARIANTS = [
     ("pair fine, light arrive", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="128")),
     ("pair coarse, light arrive", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="160")),
     ("pair coarse, light, 8 replicas", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="160", HOLD_TC_WCOPIES="8")),
+    ("pair wide epilogue, light", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="384")),
+    ("pair wide, light, 8 replicas", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="384", HOLD_TC_WCOPIES="8")),
 ]
 ctx = capi.Context(0); dev = torch.device("cuda", 0)
 sc = synth.make_scene(H=8, W=8, S=128, nodes=("right", "object"))
