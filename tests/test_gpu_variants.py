@@ -58,6 +58,8 @@ def impl_render_matches_default(ctx):
     ("fast", dict(HOLD_TC_FAST="1")),
     ("pair_coarse", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="32")),
     ("pair_light", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="160")),
+    ("pair_wide", dict(HOLD_TC_PAIR="1", HOLD_TC_DBG="384")),
+    ("fast_replicas", dict(HOLD_TC_FAST="1", HOLD_TC_WCOPIES="4")),
 ])
 def test_sdf_kernel_variant(isolated, name, env):
     isolated("tests/test_gpu_variants.py", "impl_sdf_kernels_match_fp32", env=env)
