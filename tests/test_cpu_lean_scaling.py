@@ -92,3 +92,73 @@ def test_operand_scaling_schemes_match_fp64():
         got = _run(Ws, bs, x, scheme)
         err = np.abs(got - exact).max() / max(1.0, np.abs(exact).max())
         assert err < 3e-6, f"{scheme}: {err:.2e}"
+
+
+def test_reverse_mode_chain_with_t_stash_matches_autograd():
+    """The algebra of the FAST reverse-mode kernel (mlp_tc_fast.cuh: LEAN forward, stash of t, softplus' = sigmoid_t(t) evaluated
+    in the backward rounds, seed 64/(ln2/100) * w_t * s_7, transposed images at the plain 2^10 / 2^6 scales, embedding columns
+    chained with d embed / d x) emulated with the same split-operand products: sdf, gradient and feature against fp64 autograd."""
+    sd = synth.make_sdf_state("hand", 0, 0.45)
+    Ws, bs = _folded(sd, "hand")
+    g = torch.Generator().manual_seed(2)
+    x = ((torch.rand(200, 3, generator=g) - 0.5) * 1.6).double()
+    # fp64 autograd reference
+    xt = x.clone().requires_grad_()
+    def emb_t(v):
+        out = [v]
+        for k in range(6):
+            out += [torch.sin(v * 2.0**k), torch.cos(v * 2.0**k)]
+        return torch.cat(out, -1)
+    h = emb_t(xt)
+    for l in range(8):
+        z = h @ torch.from_numpy(Ws[l]).T + torch.from_numpy(bs[l])
+        h = torch.nn.functional.softplus(z, beta=100)
+        if l == 3:
+            h = torch.cat([h[:, :217], emb_t(xt)], 1)
+    out8 = h @ torch.from_numpy(Ws[8]).T + torch.from_numpy(bs[8])
+    sdf_ref = out8[:, 0]
+    grad_ref = torch.autograd.grad(sdf_ref.sum(), xt)[0].numpy()
+    feat_ref, sdf_ref = out8[:, 1:].detach().numpy(), sdf_ref.detach().numpy()
+    # ---- emulation
+    xn = x.numpy()
+    emb = _embed(xn).astype(np.float32)
+    demb = np.zeros((xn.shape[0], 39, 3), np.float32)           # d embed_e / d x_d (embedders.py layout)
+    for e in range(39):
+        d = e % 3
+        if e < 3:
+            demb[:, e, d] = 1.0
+        else:
+            qq = (e - 3) // 3
+            f = 2.0 ** (qq >> 1)
+            demb[:, e, d] = (-f * np.sin(xn[:, d] * f)) if (qq & 1) else (f * np.cos(xn[:, d] * f))
+    sigmoid_t = lambda t: np.where(t >= 0, 1.0 / (1.0 + np.exp2(-np.abs(t))), np.exp2(-np.abs(t)) / (1.0 + np.exp2(-np.abs(t)))).astype(np.float32)
+    a, stash = 64.0 * emb, []
+    for l in range(8):
+        cs = np.full(Ws[l].shape[1], ACT * 2.0**17)
+        if l == 0:
+            cs[:] = 2.0**11
+        if l == 4:
+            cs[217:] = 2.0**11
+        t = _mm3(a, Ws[l] * cs[None, :]) * np.float32(LOG2E100 / 2.0**17) + (LOG2E100 * bs[l]).astype(np.float32)
+        stash.append(t)
+        S = (np.maximum(t, 0) + np.log2(1.0 + np.exp2(-np.abs(t.astype(np.float64))))).astype(np.float32)
+        a = np.concatenate([S[:, :217], 64.0 * emb], 1) if l == 3 else S
+    sdf = a.astype(np.float64) @ (Ws[8][0] * ACT) + bs[8][0]
+    feat = _mm3(a, Ws[8][1:] * (ACT * 2.0**17)) * np.float32(2.0**-17) + bs[8][1:].astype(np.float32)
+    gA = (np.float32(64.0 / ACT) * (Ws[8][0] * ACT).astype(np.float32)[None, :] * sigmoid_t(stash[7])).astype(np.float32)   # 64 * g_7
+    grad = np.zeros((xn.shape[0], 3), np.float64)
+    for l in range(7, -1, -1):
+        acc = _mm3(gA, 1024.0 * Ws[l].T) * np.float32(2.0**-16)          # g_l . W_l over the transposed image
+        if l == 4:
+            grad += np.einsum("pe,ped->pd", acc[:, 217:].astype(np.float64), demb)
+            acc = acc.copy()
+            acc[:, 217:] = 0.0
+        if l == 0:
+            grad += np.einsum("pe,ped->pd", acc[:, :39].astype(np.float64), demb)
+            break
+        gA = (64.0 * acc[:, : Ws[l - 1].shape[0]] * sigmoid_t(stash[l - 1])).astype(np.float32)
+        if Ws[l - 1].shape[0] < 256:                                         # layer 3 has 217 outputs; its operand is 256 wide
+            gA = np.concatenate([gA, np.zeros((gA.shape[0], 256 - gA.shape[1]), np.float32)], 1)[:, : Ws[l - 1].shape[0]]
+    rel = lambda a_, b_: np.abs(a_ - b_).max() / max(1.0, np.abs(b_).max())
+    assert rel(sdf, sdf_ref) < 3e-6 and rel(feat, feat_ref) < 3e-6, (rel(sdf, sdf_ref), rel(feat, feat_ref))
+    assert rel(grad, grad_ref) < 1e-5, rel(grad, grad_ref)
