@@ -75,6 +75,7 @@ def test_background_against_reference_golden(ctx):
         assert err <= 1e-5, f"{k}: {err:.2e}"
 
 
+@pytest.mark.skipif(__import__("os").environ.get("HOLD_RUN_VARIANTS") != "1", reason="opt-in: HOLD_RUN_VARIANTS=1 (tcgen05 code without a hardware run)")
 @pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
 def test_background_tcgen05_variant_matches_fp32(ctx):
     """HOLD_BG_TC=1: the background nets on the tensor-core kernels against the exact-fp32 path (same inputs)."""

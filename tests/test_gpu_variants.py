@@ -2,10 +2,17 @@
 fresh interpreter with its switch set and held to the same bar as the default tensor-core kernels (tests/test_gpu_tc.py:
 sdf / feature / gradient within 1e-4 of the exact-fp32 CUDA-core kernels).  Non-strict xfail: XPASS = ready for A/B timing
 (tools/exp_matrix.py)."""
+import os
+
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+# Opt-in (HOLD_RUN_VARIANTS=1, set by tools/round2_first_call.sh): these drive tcgen05 / mbarrier protocols that never ran on
+# hardware; they execute in separate processes with bounded waits, but a first run belongs in a supervised GPU call, not in an
+# unattended suite that is followed by the measurements.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HOLD_RUN_VARIANTS") != "1", reason="opt-in: HOLD_RUN_VARIANTS=1"),
+              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
 
 
 def impl_sdf_kernels_match_fp32(ctx):
