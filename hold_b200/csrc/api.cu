@@ -9,8 +9,6 @@
 #include "sampler.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
-#include "mlp_tc_fast.cuh"
-#include "mlp_tc2.cuh"
 #include "composite.cuh"
 #include "background.cuh"
 #include "background_tc.cuh"
@@ -84,7 +82,7 @@ static int launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, cons
                       float* grad, float* feat, const SamplerState* st, cudaStream_t s) {
   if (P <= 0) return HOLD_OK;
   const bool jvp = (grad != nullptr) || (feat != nullptr);
-  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc2_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
+  if (ns.cfg.mlp_mode == HOLD_MLP_TC) return tc_launch_sdf(ctx, ns, P, xc, embed_w, sdf, grad, feat, st, s);
   SimtArgs a;
   memset(&a, 0, sizeof(a));
   fill_sdf_args(ns, a, jvp);
@@ -135,9 +133,7 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
     // hot path: consecutive samples of a ray per thread, KNN seeded from the previous sample
     const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
     dim3 g2(ceil_div(rays * segs, 128), B);
-    // experiment switches, read per launch so that one process can A/B them (tools/exp_matrix.py)
-    const bool knn_occ = [] { const char* e = getenv("HOLD_KNN_OCC"); return e != nullptr && atoi(e) != 0; }();
-    const bool knn_filt = [] { const char* e = getenv("HOLD_KNN_FILTER"); return e != nullptr && atoi(e) != 0; }();
+    const bool knn_occ = ctx->knn_variant == 2, knn_filt = ctx->knn_variant == 1;   // hold_debug_set(ctx, 1, v): A/B only
     if (knn_filt) k_inverse_warp_hand_rays_filt<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     else if (knn_occ) k_inverse_warp_hand_rays_occ<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
     else k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
@@ -198,8 +194,6 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_SDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
-  if (rc == HOLD_OK) rc = tc2_init();
-  if (rc == HOLD_OK) rc = tc_fast_init();
   if (rc == HOLD_OK) rc = tc_bg_init();
   if (rc) { delete ctx; return rc; }
   *out = ctx;
@@ -513,6 +507,77 @@ int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, con
   return HOLD_OK;
 }
 
+/* One iteration of the while loop of ErrorBoundSampler.get_z_vals (engine/ray_sampler.py:160-311) on caller-supplied state:
+ * the sorted (z, sdf) of the previous rounds, this round's new samples and their sdf, beta per ray.  Runs exactly the kernels
+ * hold_sample runs for round `it` (merge + d* + beta line search, then PDF -> inverse CDF), so that a round can be compared
+ * with the reference in isolation (teacher forcing): upstream last-bit differences do not propagate into it. */
+int hold_sampler_round(hold_ctx* ctx, int node, int R, int it, const float* z_old, const float* sdf_old, const float* z_new,
+                       const float* sdf_new, const float* beta_in, const float* far, const float* beta_param,
+                       float* z_merged, float* sdf_merged, float* beta_out, float* samples_out, int32_t* upsample_out,
+                       void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  NodeState& ns = ctx->nodes[node];
+  const hold_node_cfg& c = ns.cfg;
+  HOLD_REQUIRE(R >= 0 && it >= 0 && it < c.max_total_iters, "bad R / round index");
+  if (R == 0) return HOLD_OK;
+  HOLD_REQUIRE(z_new && sdf_new && beta_in && far && beta_param && beta_out && samples_out, "NULL argument");
+  HOLD_REQUIRE(it == 0 || (z_old && sdf_old), "round %d needs the previous rounds' (z, sdf)", it);
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ne = c.n_samples_eval, n_old = it * Ne, n = n_old + Ne;
+  WS(WS_Z, float, (size_t)R * kMaxZ, zb);
+  WS(WS_SDF, float, (size_t)R * kMaxZ, sb);
+  WS(WS_ZNEW, float, (size_t)R * Ne, znew);
+  WS(WS_SDFNEW, float, (size_t)R * Ne, sdfnew);
+  WS(WS_BETA, float, R, betab);
+  WS(WS_FAR, float, R, farb);
+  WS(WS_ZTMP, float, (size_t)R * 512, zfin);
+  if (n_old > 0) {
+    HOLD_CUDA(cudaMemcpy2DAsync(zb, kMaxZ * sizeof(float), z_old, n_old * sizeof(float), n_old * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
+    HOLD_CUDA(cudaMemcpy2DAsync(sb, kMaxZ * sizeof(float), sdf_old, n_old * sizeof(float), n_old * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
+  }
+  HOLD_CUDA(cudaMemcpyAsync(znew, z_new, (size_t)R * Ne * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemcpyAsync(sdfnew, sdf_new, (size_t)R * Ne * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemcpyAsync(betab, beta_in, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemcpyAsync(farb, far, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemsetAsync(ns.sstate, 0, sizeof(SamplerState), s));
+  SamplerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R, a.rays_per_frame = R;
+  a.n_eval = Ne, a.n_samples = c.n_samples, a.n_extra = c.n_samples_extra, a.beta_iters = c.beta_iters, a.max_iters = c.max_total_iters;
+  a.eps = c.eps, a.add_tiny = c.add_tiny, a.near = c.near, a.r_sphere = c.bounding_sphere, a.beta_min = c.beta_min;
+  a.beta_param = beta_param;
+  a.z = zb, a.sdf = sb, a.znew = znew, a.sdfnew = sdfnew, a.beta = betab, a.far = farb, a.st = ns.sstate, a.err = ctx->dev_err;
+  a.z_out = zfin, a.iters_out = nullptr;
+  const int wpb = 4;
+  const int samp_smem = wpb * 6 * kMaxZ * (int)sizeof(float);
+  k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+  HOLD_LAUNCH_CHECK(ctx);
+  if (z_merged) HOLD_CUDA(cudaMemcpy2DAsync(z_merged, n * sizeof(float), zb, kMaxZ * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
+  if (sdf_merged) HOLD_CUDA(cudaMemcpy2DAsync(sdf_merged, n * sizeof(float), sb, kMaxZ * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
+  HOLD_CUDA(cudaMemcpyAsync(beta_out, betab, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+  HOLD_LAUNCH_CHECK(ctx);
+  // upsample decision of this round (ray_sampler.py:244-246), read back for the caller: it sizes samples_out
+  unsigned int bits = 0;
+  float b0 = 0.f;
+  HOLD_CUDA(cudaMemcpyAsync(&bits, &ns.sstate->beta_max_bits[it], sizeof(bits), cudaMemcpyDeviceToHost, s));
+  HOLD_CUDA(cudaMemcpyAsync(&b0, beta_param, sizeof(float), cudaMemcpyDeviceToHost, s));
+  HOLD_CUDA(cudaStreamSynchronize(s));
+  float bm;
+  memcpy(&bm, &bits, sizeof(bm));
+  const bool upsample = (bm > fabsf(b0) + c.beta_min) && (it + 1 < c.max_total_iters);
+  if (upsample_out) *upsample_out = upsample ? 1 : 0;
+  if (upsample) {
+    HOLD_CUDA(cudaMemcpyAsync(samples_out, znew, (size_t)R * Ne * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    const int S = c.n_samples + c.n_samples_extra + 2;
+    HOLD_CUDA(cudaMemcpyAsync(samples_out, zfin, (size_t)R * S * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return HOLD_OK;
+}
+
 int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_loc, const float* ray_dirs,
                const hold_node_pose* pose, const hold_factors* out, void* stream) {
   int rc = check_node(ctx, node, true);
@@ -792,6 +857,15 @@ int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
   return HOLD_OK;
 }
 
+/* debug/test hook (not in the public header): 1 = hand KNN kernel variant for A/B runs (0 default, 1 filtered scan, 2 occupancy) */
+int hold_debug_set(hold_ctx* ctx, int key, int value) {
+  if (!ctx) return HOLD_E_BADARG;
+  if (key == 1) ctx->knn_variant = value;
+  else if (key == 2) ctx->tc_acc_comp = value;
+  else return HOLD_E_BADARG;
+  return HOLD_OK;
+}
+
 /* debug/test hook (not in the public header): workspace slot pointers of the last call */
 int hold_debug_ws_copy(hold_ctx* ctx, int slot, void* dst, size_t bytes) {
   if (!ctx || slot < 0 || slot >= 24 || ctx->ws[slot].bytes < bytes) return HOLD_E_BADARG;
@@ -800,7 +874,7 @@ int hold_debug_ws_copy(hold_ctx* ctx, int slot, void* dst, size_t bytes) {
   return HOLD_OK;
 }
 
-int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, void* stream) {
+int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, int mlp_mode, void* stream) {
   HOLD_REQUIRE(ctx && sdf && rgb, "NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
   HOLD_REQUIRE(sdf->n_layers == 9 && rgb->n_layers == 2, "background nets: 9 + 2 layers expected");
@@ -838,8 +912,9 @@ int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_m
   if ((rc = dev_alloc(&c.b_last, 4))) return rc;
   k_pack_rows<<<3, 128, 0, s>>>(rgb->weight_v[1], rgb->weight_g[1], rgb->bias[1], 128, 0, 3, c.w_last, c.b_last);
   HOLD_LAUNCH_CHECK(ctx);
-  { const char* e = getenv("HOLD_BG_TC");   // tcgen05 images only for the experimental path
-    if (e != nullptr && atoi(e) != 0 && (rc = tc_bg_pack(ctx, ctx->bg_tc, sdf, rgb, s))) return rc; }
+  HOLD_REQUIRE(mlp_mode == HOLD_MLP_FP32 || mlp_mode == HOLD_MLP_TC, "bad mlp_mode");
+  ctx->bg_mlp_mode = mlp_mode;
+  if (mlp_mode == HOLD_MLP_TC && (rc = tc_bg_pack(ctx, ctx->bg_tc, sdf, rgb, s))) return rc;
   ctx->has_bg = true;
   return HOLD_OK;
 }
@@ -875,8 +950,7 @@ int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const flo
       a.n_layers = 9;
       for (int l = 0; l < 9; ++l) { a.L[l].Wt = ctx->bg_sdf.Wt[l], a.L[l].bias = ctx->bg_sdf.bias[l], a.L[l].Kpad = ctx->bg_sdf.Kpad[l], a.L[l].N = ctx->bg_sdf.N[l]; }
       a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last, a.sdf = sdf_ws, a.feat = feat_ws;
-      static const bool bg_tc = [] { const char* e = getenv("HOLD_BG_TC"); return e != nullptr && atoi(e) != 0; }();
-      if (bg_tc && ctx->bg_tc != nullptr) {
+      if (ctx->bg_mlp_mode == HOLD_MLP_TC && ctx->bg_tc != nullptr) {
         int rc = tc_bg_launch(ctx, *ctx->bg_tc, P, a.cam, a.dirs, a.frame_code, a.r_sphere, sdf_ws, feat_ws, rgb_ws, s);
         if (rc) return rc;
       } else {

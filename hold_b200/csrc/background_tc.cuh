@@ -1,7 +1,7 @@
-// tcgen05 variant of the background nets (HOLD_BG_TC=1; default is the exact-fp32 CUDA-core path of background.cuh):
+// tcgen05 path of the background nets (hold_bg_set_weights(..., HOLD_MLP_TC); HOLD_MLP_FP32 = the exact-fp32 CUDA-core path of background.cuh):
 // k_mlp_tc<MLP_BG_SDF> = inverted-sphere point + PE-10 + frame code -> 8 x 256 Softplus(100) layers (skip at 4) -> sdf head
 // + 256-d feature; k_mlp_tc<MLP_BG_RGB> = [feature | view PE-4 | frame code] (315) -> 128 ReLU -> 3 sigmoid.  Same fp16
-// hi/lo split arithmetic as the foreground nets.  No hardware run yet (written after the round-1 GPU budget was spent).
+// hi/lo split arithmetic as the foreground nets (first hardware run in round 2: parity with the fp32 path green).
 #pragma once
 #include "background.cuh"
 #include "mlp_tc.cuh"
@@ -47,12 +47,12 @@ static int tc_bg_pack(hold_ctx* ctx, TcBg*& tp, const hold_mlp_weights* sdf, con
     t.sdf_nst[l] = kpad / 32;
     if (!t.sdf_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_img[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
-    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], nullptr, sdf->in_dim[l], row_off, N, K, kpad, scale, 0, kTcScaleW, kTcScaleW, 0, t.sdf_img[l]);
+    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], nullptr, sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
   const int K0 = kBgView + kBgFrame + kFeat;   // 315 -> 320
   if (!t.rgb_img) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img, (size_t)10 * kTcStageBytes));
-  k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[0], nullptr, K0, 0, 128, K0, 320, 1.0f, kBgView + kBgFrame, kTcScaleW, kTcScaleW, 0, t.rgb_img);
+  k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[0], nullptr, K0, 0, 128, K0, 320, 1.0f, kBgView + kBgFrame, t.rgb_img);
   HOLD_LAUNCH_CHECK(ctx);
   if (!t.rgb_w_last) HOLD_CUDA(cudaMalloc((void**)&t.rgb_w_last, 3 * 256 * sizeof(float)));
   k_pad_rows<<<3, 256, 0, s>>>(ctx->bg_rgb.w_last, 3, 128, 256, t.rgb_w_last);
@@ -72,7 +72,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   }
   a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last;
   a.cam = cam, a.dirs = dirs, a.frame_code = frame_code, a.r_sphere = r_sphere;
-  a.sdf = sdf, a.feat = feat, a.err = ctx->dev_err;
+  a.sdf = sdf, a.feat = feat, a.err = ctx->dev_err, a.unscale = kTcUnscale;
   const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
   k_mlp_tc<MLP_BG_SDF><<<grid, kTcThreadsTotal, TcCfg<MLP_BG_SDF>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
@@ -81,7 +81,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   c.P = P, c.n_layers = 1, c.pts_per_frame = P;
   c.L[0].wimg = t.rgb_img, c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].nst = 10, c.L[0].N = 256;
   c.w_last = t.rgb_w_last, c.b_last = ctx->bg_rgb.b_last;
-  c.dirs = dirs, c.frame_code = frame_code, c.feat = feat, c.rgb = rgb, c.err = ctx->dev_err;
+  c.dirs = dirs, c.frame_code = frame_code, c.feat = feat, c.rgb = rgb, c.err = ctx->dev_err, c.unscale = kTcUnscale;
   c.k0 = kBgView + kBgFrame + kFeat;
   k_mlp_tc<MLP_BG_RGB><<<grid, kTcThreadsTotal, TcCfg<MLP_BG_RGB>::kSmemBytes, s>>>(c);
   HOLD_LAUNCH_CHECK(ctx);

@@ -72,7 +72,10 @@ struct hold_ctx {
   hold::Buffer ws[24];  // grow-only workspaces, indexed by purpose (api.cu)
   hold::PackedMlp bg_sdf, bg_rgb;  // background nets (fp32 CUDA-core layout)
   bool has_bg = false;
+  int bg_mlp_mode = 0;             // HOLD_MLP_* of the background nets (hold_bg_set_weights)
   hold::TcBg* bg_tc = nullptr;
+  int knn_variant = 0;             // A/B hook (hold_debug_set), 0 = production kernel
+  int tc_acc_comp = 0;             // experiment hook (hold_debug_set key 2): accumulator scale 1 + c * 2^-24 in the SDF chains
 };
 
 namespace hold {

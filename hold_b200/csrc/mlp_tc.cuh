@@ -13,8 +13,11 @@
 // 1e-4 parity bar needs: an sdf error eps reaches the density as eps/beta^2 (beta down to 1e-2), so plain bf16
 // (2^-9) and even a bf16 split (2^-16, measured 83 % of pixels within 1e-4) do not meet it (SURVEY §7 "hard
 // parts").  Range: |x| must stay below 65504 (activations/weights here are O(1e-3..1e2)).  The sdf / rgb heads (1 resp. 3 output
-// rows) are fp32 dot products in the epilogue.  Gradients: reverse mode in the same kernel (MODE 3, default); forward
-// mode with 4 rows per point (MODE 1, HOLD_TC_GRAD=jvp) is kept for A/B.
+// rows) are fp32 dot products in the epilogue.  Gradients: reverse mode in the same kernel (MODE MLP_SDF_REV): the forward
+// epilogues stash softplus'(z_l) as unorm16 (512 KB per CTA: 76 MB for the grid, L2-resident; quantisation step 1.5e-5 moves
+// the gradient by <= 1.2e-5 of its scale, tests/test_cpu_stash_quant.py), the backward layers run over transposed weight images.
+// Round-2 A/B on hardware (profiles/r02_variants.md) retired the other variants (base-2-domain epilogue, rebuilt 16-column
+// epilogue, CTA-pair kernels, forward-mode gradient): none beat this kernel at equal error.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -33,18 +36,6 @@ constexpr int kTcThreads = 192;
 // rescaled by 2^-16 in the epilogue's bias FMA.  Range: |a| < 1023, |w| < 64.
 constexpr float kTcScaleA = 64.0f, kTcScaleW = 1024.0f, kTcUnscale = 1.0f / (64.0f * 1024.0f);
 
-// LEAN variant (HOLD_TC_LEAN=1, SDF chains): the epilogue works in the base-2 domain of Softplus(beta=100),
-//   softplus(z) = (ln2/100) * S(t),  t = 100 z log2(e),  S(t) = max(t, 0) + lg2(1 + 2^-|t|),
-// t comes straight out of the accumulator by ONE fma (bias pre-multiplied by 100 log2 e), S is the next layer's A
-// operand as is, and the factor ln2/100 lives in the next layer's weight image (columns fed by activations: W * ln2/100 *
-// 2^17; columns fed by the embedding, A = 64 embed: W * 2^11; accumulator = 2^17 z either way).  6 instead of 8
-// instructions per element, same two MUFU ops.
-constexpr float kLeanAccToT = 144.26950408889634f / 131072.0f;      // accumulator (2^17 z) -> t
-constexpr float kLeanAccToZ = 1.0f / 131072.0f;                      // accumulator -> z (feature layer)
-constexpr float kLeanBiasToT = 144.26950408889634f;                  // bias -> bias_t
-constexpr float kLeanAct = 0.6931471805599453f * 0.01f;              // S -> softplus
-constexpr float kLeanWAct = kLeanAct * 131072.0f, kLeanWEmb = 2048.0f;  // weight image scales per input column type
-
 constexpr int kTcMaxSteps = 17;
 struct TcLayer {
   const uint8_t* wimg;  // pre-swizzled stage images, nst * 32 KB
@@ -59,13 +50,6 @@ __global__ void k_scale_vec(const float* __restrict__ src, int n, float c, float
 }
 
 struct TcMlp {
-  uint8_t* sdf_imgL[HOLD_MAX_LAYERS] = {nullptr};  // LEAN images of layers 0..8 (per-column operand scales)
-  float* sdf_bias_t[8] = {nullptr};                 // LEAN: bias * 100 log2(e), layers 0..7
-  float* w_last_t = nullptr;                        // LEAN: sdf head row * ln2/100
-  uint8_t* sdf_imgL_rep[HOLD_MAX_LAYERS] = {nullptr};   // HOLD_TC_WCOPIES: [copies][nst * 32 KB] replicas of sdf_imgL / sdf_imgT
-  uint8_t* sdf_imgT_rep[HOLD_MAX_LAYERS] = {nullptr};
-  uint8_t* sdf_img_rep[HOLD_MAX_LAYERS] = {nullptr};    // replicas of the plain images (pair kernel)
-  int rep_copies = 0;
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient
@@ -75,7 +59,7 @@ struct TcMlp {
 struct TcArgs {
   int P, n_layers;
   TcLayer L[kTcMaxSteps];
-  float* sig;  // reverse mode: per-CTA stash of softplus'(z_l), [grid][8][128][256] fp32
+  uint16_t* sig;  // reverse mode: per-CTA stash of softplus'(z_l) as unorm16, [grid][8][128][256]
   const float* w_last;
   const float* b_last;
   const float* xc;
@@ -90,17 +74,11 @@ struct TcArgs {
   float* rgb;
   const SamplerState* st;
   int* err;
-  int dbg;  // experiment switches (HOLD_TC_DBG): 1 = skip the hi*lo pass, 2 = ReLU instead of softplus, 4 = skip lo*hi too,
-            // 8 = no weight copies (stale smem as weights: timing only), 16 = weight ring of depth 3 (pair kernel),
-            // 32 = coarse hand-offs (pair kernel), 64 = LEAN reverse mode stashes t and computes softplus' in the backward rounds,
-            // 128 = pair kernel: hand-off arrivals with CTA-scope release (CUTLASS ClusterBarrier form) instead of release.cluster,
-            // 256 = pair kernel, sampler rounds: FAST-shaped epilogue (2 rounds of 16 columns, coarse hand-offs)
   const float* cam;          // background modes: ray origins / directions [R,3] of this frame chunk, its frame code [32]
   const float* dirs;
   const float* frame_code;
   float r_sphere;
-  int wcopies;               // FAST kernels, HOLD_TC_WCOPIES=N: CTA b streams weight-image copy b % N (spreads the L2 hot lines)
-  long long* prof;  // pair kernel, HOLD_TC_PROF=1: cycle accounting of cluster 0 (see mlp_tc2.cuh)
+  float unscale;             // accumulator -> value: kTcUnscale (times the experimental compensation factor, hold_debug_set key 2)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -230,19 +208,14 @@ __device__ __forceinline__ float softplus100_fast(float z, float& u_out) {
   return fmaf(L, 0.6931471805599453f * 0.01f * kTcScaleA, fmaxf(z, 0.f) * kTcScaleA);
 }
 
-// S(t) of the LEAN variant; u_out = 2^-|t| for the derivative
-__device__ __forceinline__ float softplus_t(float t, float& u_out) {
-  const float u = mufu_ex2(-fabsf(t));
-  u_out = u;
-  return fmaxf(t, 0.f) + mufu_lg2(1.0f + u);
+// unorm16 stash of softplus' in [0, 1]: encode by the magic-number add (round to nearest, no F2I), decode by OR-ing the
+// 16 bits into the mantissa of 2^23.  q = round(65535 s); decode returns q as a float (the caller folds 1/65535 into its scale).
+__device__ __forceinline__ uint32_t unorm16_pack2(float s0, float s1) {
+  const uint32_t b0 = __float_as_uint(fmaf(s0, 65535.0f, 8388608.0f)), b1 = __float_as_uint(fmaf(s1, 65535.0f, 8388608.0f));
+  return __byte_perm(b0, b1, 0x5410);
 }
-
-// softplus'(z) = sigmoid(100 z) from t = 100 z log2(e): 2^t / (1 + 2^t), overflow-free
-__device__ __forceinline__ float sigmoid_t(float t) {
-  const float u = mufu_ex2(-fabsf(t));
-  const float r = mufu_rcp(1.0f + u);
-  return (t >= 0.f) ? r : u * r;
-}
+__device__ __forceinline__ float unorm16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8388608.0f; }
+__device__ __forceinline__ float unorm16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8388608.0f; }
 
 // One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
 // w.r.t. coordinate comp-1.  Deliberately NOT inlined: it is called from rolled loops at the tile prologue and
@@ -320,32 +293,14 @@ struct TcCfg {
   static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
 };
 
-// PROF (HOLD_TC_PROF=1, sampler-round kernel only): CTA 0 accounts the cycles its role warps spend waiting, into a.prof:
-// [0] MMA warp total, [1] waiting for hand-offs, [2] waiting for weight stages; [8] producer total, [9] waiting for a free
-// stage; [16] epilogue warp 2 total, [17] waiting for the accumulator; [20], [21] the same for epilogue warp 17.
-template <bool PROF>
-__device__ __forceinline__ bool mbar_wait_p(uint32_t bar, uint32_t parity, int* err, int tag, volatile int* abort_flag, bool on,
-                                            long long& acc) {
-  if (!PROF || !on) return mbar_wait(bar, parity, err, tag, abort_flag);
-  const long long t0 = clock64();
-  const bool ok = mbar_wait(bar, parity, err, tag, abort_flag);
-  acc += clock64() - t0;
-  return ok;
-}
-
-template <int MODE, bool LEAN = false, bool PROF = false>
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
-  static_assert(!LEAN || MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV, "LEAN: SDF chains only");
-  static_assert(!PROF || MODE == MLP_SDF_ONLY, "PROF: sampler-round kernel only");
+  static_assert(MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV || MODE == MLP_COLOR || MODE == MLP_BG_SDF || MODE == MLP_BG_RGB, "chains built on tcgen05");
   if (a.st != nullptr && a.st->done) return;
-  const bool prof_on = PROF && a.prof != nullptr && blockIdx.x == 0;
-  long long tp0 = 0, tp1 = 0;
-  const long long t_begin = prof_on ? clock64() : 0;
   using Cfg = TcCfg<MODE>;
   constexpr bool kColorLike = Cfg::kColorLike;
   constexpr int NA = Cfg::kAChunks, NS = Cfg::kStages, NHO = Cfg::kHandoffs;
-  constexpr int RPP = (MODE == MLP_SDF_JVP) ? 4 : 1;
-  constexpr int PPT = kTcRows / RPP;
+  constexpr int PPT = kTcRows;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
@@ -382,21 +337,16 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         for (int l = 0; l < a.n_layers; ++l) {
           const uint8_t* src = a.L[l].wimg;
           for (int s = 0; s < a.L[l].nst; ++s) {
-            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag, prof_on, tp0))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait(bWEmpty + 8 * stage, phase ^ 1, a.err, 1, abort_flag))) goto tc_done;
             if (elect_one()) {
-              if (a.dbg & 8) {
-                mbar_arrive(bWFull + 8 * stage);
-              } else {
-                mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
-                bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
-              }
+              mbar_expect_tx(bWFull + 8 * stage, kTcStageBytes);
+              bulk_g2s(sW + stage * kTcStageBytes, src + (size_t)s * kTcStageBytes, kTcStageBytes, bWFull + 8 * stage);
             }
             __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
-      if (PROF && prof_on && lane == 0) { a.prof[8] = clock64() - t_begin; a.prof[9] = tp0; }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer (whole warp walks the loop, one elected lane issues)
@@ -411,9 +361,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           for (int s = 0; s < nst; ++s) {
             const int c = s >> 1;  // 64-wide A chunk holding this 32-k stage
             // hand-off s = columns [32 s, 32 s + 32) of the previous layer's activations
-            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag, prof_on, tp0))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait(bAReady + 8 * s, (a_par >> s) & 1, a.err, 2, abort_flag))) goto tc_done;
             a_par ^= (1u << s);
-            if (!__all_sync(0xffffffffu, mbar_wait_p<PROF>(bWFull + 8 * stage, phase, a.err, 3, abort_flag, prof_on, tp1))) goto tc_done;
+            if (!__all_sync(0xffffffffu, mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag))) goto tc_done;
             tc_fence_after();
             const uint32_t wb = sW + stage * kTcStageBytes;
             const bool el = elect_one();
@@ -426,8 +376,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
               if (el) {
                 tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
-                if (!(a.dbg & 4)) tc_mma(d_tmem, alo, whi, kIdescF16, 1);
-                if (!(a.dbg & 1)) tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
+                tc_mma(d_tmem, alo, whi, kIdescF16, 1);
+                tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
               }
             }
             if (el) tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
@@ -438,7 +388,6 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           __syncwarp();
         }
       }
-      if (PROF && prof_on && lane == 0) { a.prof[0] = clock64() - t_begin; a.prof[1] = tp0; a.prof[2] = tp1; }
     }
   } else {
     // ============================================================ epilogue: kTcW warps per TMEM lane quarter; warp
@@ -451,11 +400,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
     uint8_t* gA_hi = gen_base;
     uint8_t* gA_lo = gen_base + NA * kTcAChunkBytes;
     float* scratch = reinterpret_cast<float*>(gen_base);  // head partial sums (A region, free at tile end)
-    const int comp = row % RPP;
-    const bool is_value = (comp == 0);
     uint32_t d_par = 0;  // bit b = parity to wait for on d_full[b]
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int p = tile * PPT + row / RPP;
+      const int p = tile * PPT + row;
       const bool valid = p < a.P;
       float px = 0.f, py = 0.f, pz = 0.f, pw = 0.f;
       // ---------------------------------------------------------- prologue: layer-0 A operand (this warp's columns)
@@ -492,7 +439,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         for (int h = 0; h < 2; ++h) {
           float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(h * 32 + sub * 8 + i, comp, px, py, pz, a.embed_w);
+          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(h * 32 + sub * 8 + i, 0, px, py, pz, a.embed_w);
           uint4 hi, lo;
           split8(x, hi, lo);
           const int j = h * 4 + sub;
@@ -550,18 +497,25 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         // ======== reverse-mode gradient: 8 forward layers (stash softplus'), feature layer, 8 backward layers ========
         // d sdf/d z_7 = w_sdf * s_7;  d sdf/d z_{l-1} = (g_l . W_l) * s_{l-1};  embedding columns (skip input of
         // layer 4, input of layer 0) collect d sdf/d embed, chained with d embed/d x_c per column.
-        float* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
+        // Stash: s_l = softplus'(z_l) as unorm16, written and later read by the SAME thread (row, 8 columns per hand-off), L2
+        // only (.cg): 512 KB per CTA.  Reads run two hand-offs ahead of their use (an L2 round trip is ~1 hand-off long).
+        uint16_t* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
+        constexpr float kInvQ = 1.0f / 65535.0f;
         for (int st = 0; st < 17; ++st) {
           const int kind = (st < 8) ? 0 : ((st == 8) ? 1 : ((st < 16) ? 2 : 3));
           const int l = (st <= 8) ? st : 16 - st;
-          const float* bias = a.L[st].bias;
-          // per-hand-off side input: bias (forward / feature) or the stashed softplus'(z_{l-1}) (backward), always
-          // requested one hand-off ahead (first one before the accumulator wait)
-          const float* side = (kind <= 1) ? bias : ((kind == 2) ? sig + (size_t)(l - 1) * (kTcRows * 256) : nullptr);
+          const float* bias = (kind <= 1) ? a.L[st].bias : nullptr;
+          // stash row read by this step: s_7 for the feature layer's seed, s_{l-1} for backward layer l
+          const uint16_t* srow = (kind == 1) ? sig + (size_t)7 * (kTcRows * 256) : ((kind == 2) ? sig + (size_t)(l - 1) * (kTcRows * 256) : nullptr);
           float4 nb0 = make_float4(0.f, 0.f, 0.f, 0.f), nb1 = nb0;
-          if (side != nullptr) {
-            nb0 = *reinterpret_cast<const float4*>(side + sub * 8);
-            nb1 = *reinterpret_cast<const float4*>(side + sub * 8 + 4);
+          uint4 sq0 = make_uint4(0u, 0u, 0u, 0u), sq1 = sq0;
+          if (bias != nullptr) {
+            nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));
+            nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
+          }
+          if (srow != nullptr) {
+            sq0 = __ldcg(reinterpret_cast<const uint4*>(srow + sub * 8));
+            sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + 32 + sub * 8));
           }
           if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) break;
           d_par ^= (1u << (st & 1));
@@ -573,37 +527,31 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           for (int h = 0; h < 8; ++h) {
             const int n0 = h * 32 + sub * 8;
             const float bv[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
-            if (side != nullptr && h + 1 < 8) {
-              nb0 = *reinterpret_cast<const float4*>(side + n0 + 32);
-              nb1 = *reinterpret_cast<const float4*>(side + n0 + 36);
+            if (bias != nullptr && h + 1 < 8) {
+              nb0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32));
+              nb1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32) + 1);
             }
+            const uint4 sq = sq0;
+            sq0 = sq1;
+            if (srow != nullptr && h + 2 < 8) sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + n0 + 64));
             tc_wait_ld();
             float acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * ((LEAN && kind <= 1) ? 1.0f : kTcUnscale);
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * a.unscale;
             if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
             float out[8];
             if (kind == 0) {
               float sg[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float e, z;
-                if (LEAN) {
-                  z = fmaf(acc[i], kLeanAccToT, bv[i]);   // t (same sign as z)
-                  out[i] = softplus_t(z, e);
-                } else {
-                  z = acc[i] + bv[i];
-                  out[i] = softplus100_fast(z, e);
-                }
-                if (LEAN && (a.dbg & 64)) {
-                  sg[i] = z;   // stash t; softplus' is computed where it is consumed (backward rounds: idle MUFU pipe)
-                } else {
-                  const float r = mufu_rcp(1.0f + e);
-                  sg[i] = (z >= 0.f) ? r : e * r;
-                }
+                float e;
+                const float z = acc[i] + bv[i];
+                out[i] = softplus100_fast(z, e);
+                const float r = mufu_rcp(1.0f + e);
+                sg[i] = (z >= 0.f) ? r : e * r;
               }
-              *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-              *reinterpret_cast<float4*>(sig + (size_t)l * (kTcRows * 256) + n0 + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+              __stcg(reinterpret_cast<uint4*>(sig + (size_t)l * (kTcRows * 256) + n0),
+                     make_uint4(unorm16_pack2(sg[0], sg[1]), unorm16_pack2(sg[2], sg[3]), unorm16_pack2(sg[4], sg[5]), unorm16_pack2(sg[6], sg[7])));
               if (l == 3 && n0 + 8 > 217) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -616,52 +564,50 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
                   head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
                 }
               }
-            } else if (kind == 1) {
-              if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
-                const float fs = LEAN ? kLeanAccToZ : 1.0f;
-                dst[0] = make_float4(fmaf(acc[0], fs, bv[0]), fmaf(acc[1], fs, bv[1]), fmaf(acc[2], fs, bv[2]), fmaf(acc[3], fs, bv[3]));
-                dst[1] = make_float4(fmaf(acc[4], fs, bv[4]), fmaf(acc[5], fs, bv[5]), fmaf(acc[6], fs, bv[6]), fmaf(acc[7], fs, bv[7]));
-              }
-              float4 s0 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0);
-              float4 s1 = *reinterpret_cast<const float4*>(sig + (size_t)7 * (kTcRows * 256) + n0 + 4);
-              if (LEAN && (a.dbg & 64)) {
-                s0 = make_float4(sigmoid_t(s0.x), sigmoid_t(s0.y), sigmoid_t(s0.z), sigmoid_t(s0.w));
-                s1 = make_float4(sigmoid_t(s1.x), sigmoid_t(s1.y), sigmoid_t(s1.z), sigmoid_t(s1.w));
-              }
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
-              // g_7 = w_sdf * s_7, times the operand scale (LEAN: a.w_last holds w_sdf * ln2/100)
-              constexpr float ks = LEAN ? (kTcScaleA / kLeanAct) : kTcScaleA;
-              out[0] = ks * w0.x * s0.x, out[1] = ks * w0.y * s0.y, out[2] = ks * w0.z * s0.z, out[3] = ks * w0.w * s0.w;
-              out[4] = ks * w1.x * s1.x, out[5] = ks * w1.y * s1.y, out[6] = ks * w1.z * s1.z, out[7] = ks * w1.w * s1.w;
-            } else if (kind == 2) {
+            } else {
+              // softplus' of this hand-off's 8 columns (times 65535; the scale is folded below)
+              const float sv[8] = {unorm16_lo(sq.x), unorm16_hi(sq.x), unorm16_lo(sq.y), unorm16_hi(sq.y),
+                                   unorm16_lo(sq.z), unorm16_hi(sq.z), unorm16_lo(sq.w), unorm16_hi(sq.w)};
+              if (kind == 1) {
+                if (valid) {   // the 256-d feature vector: written once, read once by the colour net -> streaming stores
+                  float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
+                  __stcs(dst, make_float4(acc[0] + bv[0], acc[1] + bv[1], acc[2] + bv[2], acc[3] + bv[3]));
+                  __stcs(dst + 1, make_float4(acc[4] + bv[4], acc[5] + bv[5], acc[6] + bv[6], acc[7] + bv[7]));
+                }
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                // g_7 = w_sdf * s_7, times the operand scale
 #pragma unroll
-              for (int i = 0; i < 8; ++i) out[i] = kTcScaleA * acc[i] * ((LEAN && (a.dbg & 64)) ? sigmoid_t(bv[i]) : bv[i]);
-              if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
+                for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * wv[i] * sv[i];
+              } else if (kind == 2) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (n0 + i >= 217) {
-                    const int e = n0 + i - 217, d = e % 3;
-                    const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
-                    head1 += (d == 0) ? je : 0.f;
-                    head2 += (d == 1) ? je : 0.f;
-                    gz_acc += (d == 2) ? je : 0.f;
-                    out[i] = 0.f;
+                for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * acc[i] * sv[i];
+                if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (n0 + i >= 217) {
+                      const int e = n0 + i - 217, d = e % 3;
+                      const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
+                      head1 += (d == 0) ? je : 0.f;
+                      head2 += (d == 1) ? je : 0.f;
+                      gz_acc += (d == 2) ? je : 0.f;
+                      out[i] = 0.f;
+                    }
                   }
                 }
-              }
-            } else {  // kind 3: d sdf / d embed through layer 0's input
-              if (n0 < 40) {
+              } else {  // kind 3: d sdf / d embed through layer 0's input
+                if (n0 < 40) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int e = n0 + i;
-                  if (e < kEmbed) {
-                    const int d = e % 3;
-                    const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
-                    head1 += (d == 0) ? je : 0.f;
-                    head2 += (d == 1) ? je : 0.f;
-                    gz_acc += (d == 2) ? je : 0.f;
+                  for (int i = 0; i < 8; ++i) {
+                    const int e = n0 + i;
+                    if (e < kEmbed) {
+                      const int d = e % 3;
+                      const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
+                      head1 += (d == 0) ? je : 0.f;
+                      head2 += (d == 1) ? je : 0.f;
+                      gz_acc += (d == 2) ? je : 0.f;
+                    }
                   }
                 }
               }
@@ -692,21 +638,21 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             for (int w = 0; w < kTcW; ++w) acc += scratch[(w * 4 + k) * kTcRows + row];
             hsum[k] = acc;
           }
-          a.sdf[p] = hsum[0] * (LEAN ? 1.0f : (1.0f / kTcScaleA)) + a.b_last[0];
+          a.sdf[p] = hsum[0] * (1.0f / kTcScaleA) + a.b_last[0];
           a.grad[3 * (size_t)p] = hsum[1], a.grad[3 * (size_t)p + 1] = hsum[2], a.grad[3 * (size_t)p + 2] = hsum[3];
         }
         epi_bar();
         continue;
       }
       for (int l = 0; l < a.n_layers; ++l) {
-        const bool feat_layer = (MODE == MLP_SDF_JVP || MODE == MLP_BG_SDF) && (l == a.n_layers - 1);
+        const bool feat_layer = (MODE == MLP_BG_SDF) && (l == a.n_layers - 1);
         const bool head_layer = kColorLike ? (l == a.n_layers - 1) : (l == 7);
         const bool last_mma = (l == a.n_layers - 1);
         const int N = a.L[l].N;
         const float* bias = a.L[l].bias;
         float4 nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));      // issued before the wait
         float4 nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
-        if (!mbar_wait_p<PROF>(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag, prof_on, tp0)) break;
+        if (!mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag)) break;
         d_par ^= (1u << (l & 1));
         tc_fence_after();
         const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
@@ -731,9 +677,9 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           float out[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            // accumulator -> pre-activation (undo the operand scaling, add the bias on value rows); out[] holds the
-            // next layer's operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
-            const float z = fmaf(acc[i], LEAN ? kLeanAccToT : kTcUnscale, (MODE != MLP_SDF_JVP || is_value) ? bv[i] : 0.f);
+            // accumulator -> pre-activation (undo the operand scaling, add the bias); out[] holds the next layer's
+            // operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
+            const float z = fmaf(acc[i], a.unscale, bv[i]);
             float o;
             if (kColorLike) {
               o = fmaxf(z, 0.f) * kTcScaleA;
@@ -741,16 +687,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               o = z;
             } else {
               float e = 0.f;
-              const float sp = LEAN ? softplus_t(z, e) : softplus100_fast(z, e);
-              if (MODE == MLP_SDF_JVP) {
-                // softplus'(z) of the VALUE row (lane & ~3), applied to the tangent rows
-                const float r = mufu_rcp(1.0f + e) * kTcScaleA;   // e = exp(-|100 z|)
-                const float s = (z >= 0.f) ? r : e * r;            // = kTcScaleA * sigmoid(100 z)
-                const float sv = __shfl_sync(0xffffffffu, s, lane & ~3);
-                o = is_value ? sp : z * sv;
-              } else {
-                o = sp;
-              }
+              o = softplus100_fast(z, e);
             }
             out[i] = o;
           }
@@ -758,7 +695,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               if (n0 + i >= N)
-                out[i] = kTcScaleA * ((MODE == MLP_BG_SDF) ? bg_embed_val(n0 + i - N, px, py, pz, pw) : embed_val(n0 + i - N, comp, px, py, pz, a.embed_w));
+                out[i] = kTcScaleA * ((MODE == MLP_BG_SDF) ? bg_embed_val(n0 + i - N, px, py, pz, pw) : embed_val(n0 + i - N, 0, px, py, pz, a.embed_w));
           }
           if (head_layer) {
 #pragma unroll
@@ -774,7 +711,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             }
           }
           if (feat_layer) {
-            if (valid && is_value) {
+            if (valid) {
               float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
               dst[0] = make_float4(out[0], out[1], out[2], out[3]);
               dst[1] = make_float4(out[4], out[5], out[6], out[7]);
@@ -806,22 +743,16 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           float acc = 0.f;
 #pragma unroll
           for (int w = 0; w < kTcW; ++w) acc += scratch[(w * NH + k) * kTcRows + row];
-          h[k] = acc * (LEAN ? 1.0f : (1.0f / kTcScaleA));  // the head saw activations times kTcScaleA (LEAN: S, with pre-scaled head weights)
+          h[k] = acc * (1.0f / kTcScaleA);  // the head saw activations times kTcScaleA
         }
         if (kColorLike) {
 #pragma unroll
           for (int k = 0; k < NH; ++k) a.rgb[3 * (size_t)p + k] = 1.0f / (1.0f + __expf(-(h[k] + a.b_last[k])));
         } else {
-          if (comp == 0) a.sdf[p] = h[0] + a.b_last[0];
-          else a.grad[3 * (size_t)p + comp - 1] = h[0];
+          a.sdf[p] = h[0] + a.b_last[0];
         }
       }
       epi_bar();  // scratch is overwritten by the next tile's prologue
-    }
-    if (PROF && prof_on && lane == 0 && (warp == 2 || warp == 17)) {
-      const int o = (warp == 2) ? 16 : 20;
-      a.prof[o] = clock64() - t_begin;
-      a.prof[o + 1] = tp0;
     }
   }
 tc_done:
@@ -835,11 +766,9 @@ tc_done:
 
 // ------------------------------------------------------------------------------------------------ packing
 // One stage image = [256 n x 32 k] fp16 in the SW64 K-major canonical layout, hi part then lo part.
-// W[n][k] = scale * fold(v, g)[row_off + n][colmap(k)];  colmap: k -> source column (or -1 => 0).
-// Operand scale per input column: cs_lo for k < split, cs_hi for k >= split (plain images: kTcScaleW everywhere).
+// W[n][k] = kTcScaleW * scale * fold(v, g)[row_off + n][colmap(k)];  colmap: k -> source column (or -1 => 0).
 __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N, int K,
-                          int kpad, float scale, int perm_feat_first, float cs_lo, float cs_hi, int split,
-                          uint8_t* __restrict__ img) {
+                          int kpad, float scale, int perm_feat_first, uint8_t* __restrict__ img) {
   const int n = blockIdx.x;  // 0..255
   __shared__ float red[32];
   __shared__ float f_sh;
@@ -870,7 +799,7 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
       else if (k < kFeat + perm_feat_first) src = k - kFeat;
       else src = k;
     }
-    float w = (n < N && src < K) ? ((k < split) ? cs_lo : cs_hi) * (scale * (vr[src] * f)) : 0.f;
+    float w = (n < N && src < K) ? kTcScaleW * (scale * (vr[src] * f)) : 0.f;
     __half h = __float2half_rn(w);
     __half l = __float2half_rn(w - __half2float(h));
     const int st = k >> 5, kk = k & 31;
@@ -908,12 +837,8 @@ __global__ void k_tc_pack_T(const float* __restrict__ v, const float* __restrict
 static int tc_init(hold_ctx*) {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_JVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_JVP>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
   return HOLD_OK;
 }
@@ -924,13 +849,7 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->sdf_img[l]) cudaFree(ns.tc->sdf_img[l]);
     if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
     if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
-    if (ns.tc->sdf_imgL[l]) cudaFree(ns.tc->sdf_imgL[l]);
-    if (ns.tc->sdf_imgL_rep[l]) cudaFree(ns.tc->sdf_imgL_rep[l]);
-    if (ns.tc->sdf_imgT_rep[l]) cudaFree(ns.tc->sdf_imgT_rep[l]);
-    if (ns.tc->sdf_img_rep[l]) cudaFree(ns.tc->sdf_img_rep[l]);
-    if (l < 8 && ns.tc->sdf_bias_t[l]) cudaFree(ns.tc->sdf_bias_t[l]);
   }
-  if (ns.tc->w_last_t) cudaFree(ns.tc->w_last_t);
   delete ns.tc;
   ns.tc = nullptr;
 }
@@ -945,20 +864,8 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     t.sdf_nst[l] = kpad / 32;
     if (!t.sdf_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_img[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
-    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, kTcScaleW, kTcScaleW, 0,
-                                  t.sdf_img[l]);
+    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
-    // LEAN image: layer 0 is fed by the embedding, layer 4 by activations (k < 217) and the embedding (skip), the rest by activations
-    if (!t.sdf_imgL[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgL[l], (size_t)t.sdf_nst[l] * kTcStageBytes));
-    const int split = (l == 0) ? 0 : ((l == 4) ? kHidden - kEmbed : kpad);
-    k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, kLeanWAct, kLeanWEmb, split,
-                                  t.sdf_imgL[l]);
-    HOLD_LAUNCH_CHECK(ctx);
-    if (l < 8) {
-      if (!t.sdf_bias_t[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_bias_t[l], 256 * sizeof(float)));
-      k_scale_vec<<<1, 256, 0, s>>>(ns.sdf.bias[l], 256, kLeanBiasToT, t.sdf_bias_t[l]);
-      HOLD_LAUNCH_CHECK(ctx);
-    }
   }
   for (int l = 0; l < 8; ++l) {  // W_l^T for the reverse-mode gradient (layers 7..0)
     const int K_in = (l == 0) ? kEmbed : kHidden, N_out = (l == 3) ? kHidden - kEmbed : kHidden;
@@ -971,63 +878,39 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     const int K = (l == 0) ? rgb->in_dim[0] : 256, kpad = (l == 0) ? 320 : 256;
     t.rgb_nst[l] = kpad / 32;
     if (!t.rgb_img[l]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img[l], (size_t)t.rgb_nst[l] * kTcStageBytes));
-    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 14 : 0, kTcScaleW, kTcScaleW, 0,
-                                  t.rgb_img[l]);
+    k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, K, kpad, 1.0f, l == 0 ? 14 : 0, t.rgb_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
-  if (!t.w_last_t) HOLD_CUDA(cudaMalloc((void**)&t.w_last_t, 256 * sizeof(float)));
-  k_scale_vec<<<1, 256, 0, s>>>(ns.sdf.w_last, 256, kLeanAct, t.w_last_t);
-  HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }
 
+// SDF net on P canonical points: sdf only (sampler rounds: 8 layers, sdf head), or sdf + d sdf / d x_c + 256-d feature
+// (reverse mode: 8 forward layers, feature layer, 8 backward layers over the transposed images).
 static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, const float* embed_w, float* sdf, float* grad,
                          float* feat, const SamplerState* st, cudaStream_t s) {
-  const bool jvp = (grad != nullptr) || (feat != nullptr);
+  const bool rev = (grad != nullptr) || (feat != nullptr);
   TcArgs a;
   memset(&a, 0, sizeof(a));
-  a.P = P, a.n_layers = jvp ? 9 : 8;
-  for (int l = 0; l < a.n_layers; ++l) {
+  a.P = P, a.n_layers = rev ? 17 : 8;
+  for (int l = 0; l < 9; ++l) {
     a.L[l].wimg = ns.tc->sdf_img[l], a.L[l].bias = ns.sdf.bias[l], a.L[l].nst = ns.tc->sdf_nst[l], a.L[l].N = ns.sdf.N[l];
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
-  { const char* e = getenv("HOLD_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
-  static const bool use_jvp = [] { const char* e = getenv("HOLD_TC_GRAD"); return e != nullptr && strcmp(e, "jvp") == 0; }();
-  const bool lean = [] { const char* e = getenv("HOLD_TC_LEAN"); return e != nullptr && atoi(e) != 0; }() && !(jvp && use_jvp);
-  if (lean) {  // base-2-domain epilogue: own weight images, pre-scaled biases and head row
-    for (int l = 0; l < 9; ++l) a.L[l].wimg = ns.tc->sdf_imgL[l];
-    for (int l = 0; l < 8; ++l) a.L[l].bias = ns.tc->sdf_bias_t[l];
-    a.w_last = ns.tc->w_last_t;
-  }
-  if (jvp && !use_jvp) {
-    // reverse mode: 8 forward layers, feature layer, 8 backward layers over the transposed images
+  a.unscale = kTcUnscale * (1.0f + (float)ctx->tc_acc_comp * (1.0f / 16777216.0f));
+  const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
+  if (rev) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
-    const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
     void* sig = nullptr;
-    int rc = ws_get(ctx, 12 /* WS_SIG */, (size_t)grid * 8 * kTcRows * 256 * sizeof(float), &sig);
+    int rc = ws_get(ctx, 12 /* WS_SIG */, (size_t)grid * 8 * kTcRows * 256 * sizeof(uint16_t), &sig);
     if (rc) return rc;
-    a.sig = (float*)sig;
-    a.n_layers = 17;
+    a.sig = (uint16_t*)sig;
     for (int i = 0; i < 8; ++i) {
       a.L[9 + i].wimg = ns.tc->sdf_imgT[7 - i], a.L[9 + i].bias = nullptr, a.L[9 + i].nst = 8, a.L[9 + i].N = 256;
     }
-    if (lean) k_mlp_tc<MLP_SDF_REV, true><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
-    else k_mlp_tc<MLP_SDF_REV><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
-  } else if (jvp) {
-    HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
-    int tiles = ceil_div(P, kTcRows / 4);
-    k_mlp_tc<MLP_SDF_JVP><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_JVP>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_REV><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_REV>::kSmemBytes, s>>>(a);
   } else {
-    int tiles = ceil_div(P, kTcRows);
-    if (!lean && getenv("HOLD_TC_PROF") != nullptr) {   // cycle accounting of CTA 0 (tools/prof_pair.py reads workspace slot 23)
-      void* pr = nullptr;
-      int rc = ws_get(ctx, 23 /* WS_PROF (debug) */, 64 * sizeof(long long), &pr);
-      if (rc) return rc;
-      a.prof = (long long*)pr;
-      k_mlp_tc<MLP_SDF_ONLY, false, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
-    } else if (lean) k_mlp_tc<MLP_SDF_ONLY, true><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
-    else k_mlp_tc<MLP_SDF_ONLY><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
+    k_mlp_tc<MLP_SDF_ONLY><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
@@ -1043,7 +926,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   }
   a.w_last = ns.rgb.w_last, a.b_last = ns.rgb.b_last;
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
-  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err;
+  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err, a.unscale = kTcUnscale;
   int tiles = ceil_div(P, kTcRows);
   k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);

@@ -356,9 +356,10 @@ class Background(nn.Module):
     state_dict keys: bg_implicit_network.lin<k>.{weight,bias}, bg_rendering_network.lin<k>.{weight,bias},
     frame_latent_encoder.weight (the reference's `background.*` keys)."""
 
-    def __init__(self, ctx, num_frames):
+    def __init__(self, ctx, num_frames, mlp_mode=capi.MLP_FP32):
         super().__init__()
         self.ctx = ctx
+        self.mlp_mode = mlp_mode   # arithmetic of both background nets (HOLD_MLP_FP32 exact fp32, HOLD_MLP_TC tcgen05 split precision)
         dims = [84] + [256] * 8 + [257]
         self.bg_implicit_network = nn.Module()
         for l in range(9):
@@ -374,7 +375,7 @@ class Background(nn.Module):
         rsd = dict(self.bg_rendering_network.state_dict())
         wi, k1 = capi.mlp_weights(isd, 9)
         wr, k2 = capi.mlp_weights(rsd, 2)
-        check(lib().hold_bg_set_weights(self.ctx.h, C.byref(wi), C.byref(wr), stream_ptr()))
+        check(lib().hold_bg_set_weights(self.ctx.h, C.byref(wi), C.byref(wr), self.mlp_mode, stream_ptr()))
         torch.cuda.current_stream().synchronize()
 
     @torch.no_grad()

@@ -107,3 +107,23 @@ def check_off_in_surface_points_cano_mesh(ctx, mesh_v_cano, mesh_f_cano, x_cano,
     inn = torch.empty_like(off)
     check(lib().hold_off_in_surface(ctx.h, num_pixels_total, sd.shape[1], ptr(sd), float(threshold), ptr(off), ptr(inn), stream_ptr()))
     return off.bool(), inn.bool()
+
+
+def sampler_round(node, it: int, z_new, sdf_new, beta_in, far, z_old=None, sdf_old=None):
+    """One while-loop iteration of ErrorBoundSampler.get_z_vals (engine/ray_sampler.py:160-311) on caller-supplied state
+    (hold_sampler_round).  Returns dict(z, sdf [merged], beta, samples, upsample)."""
+    R, Ne = z_new.shape
+    dev = z_new.device
+    n = (it + 1) * Ne
+    S = node.S
+    f = lambda t: None if t is None else t.float().contiguous()
+    z_new, sdf_new, beta_in, far, z_old, sdf_old = f(z_new), f(sdf_new), f(beta_in), f(far.reshape(-1)), f(z_old), f(sdf_old)
+    zm, sm = torch.empty(R, n, device=dev), torch.empty(R, n, device=dev)
+    beta_out = torch.empty(R, device=dev)
+    samples = torch.empty(R, max(Ne, S), device=dev)
+    up = C.c_int32(0)
+    beta_param = node.density.beta.detach().float().reshape(1).contiguous()
+    check(lib().hold_sampler_round(node.ctx.h, node.slot, R, it, ptr(z_old), ptr(sdf_old), ptr(z_new), ptr(sdf_new), ptr(beta_in),
+                                   ptr(far), ptr(beta_param), ptr(zm), ptr(sm), ptr(beta_out), ptr(samples), C.byref(up), stream_ptr()))
+    ncol = Ne if up.value else S
+    return dict(z=zm, sdf=sm, beta=beta_out, samples=samples.reshape(-1)[: R * ncol].reshape(R, ncol), upsample=bool(up.value))

@@ -8,13 +8,13 @@ from . import capi
 from .model import HOLDNet, Node
 
 
-def build_background(sc, ctx, seed=0):
+def build_background(sc, ctx, seed=0, mlp_mode=capi.MLP_FP32):
     """Background with hold_b200.synth.make_bg_state weights and a seeded frame-code table."""
     from . import synth
     from .model import Background
 
     dev = torch.device("cuda", ctx.device)
-    bg = Background(ctx, sc.B).to(dev)
+    bg = Background(ctx, sc.B, mlp_mode).to(dev)
     sdf_sd, rgb_sd = synth.make_bg_state(seed)
     bg.bg_implicit_network.load_state_dict(sdf_sd, strict=True)
     bg.bg_rendering_network.load_state_dict(rgb_sd, strict=True)

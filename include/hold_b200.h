@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HOLD_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define HOLD_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef enum hold_status {
   HOLD_OK = 0,
@@ -201,6 +201,17 @@ int hold_camera_rays(hold_ctx* ctx, int B, int P, const float* uv, const float* 
 int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, const float* ray_dirs,
                 const hold_node_pose* pose, const hold_sampler_rand* rnd, float* z_vals, int32_t* iters,
                 void* stream);
+
+/* One iteration of the while loop of ErrorBoundSampler.get_z_vals (engine/ray_sampler.py:160-311) on caller-supplied state
+ * ("teacher forcing": lets a test compare a single round with the reference without upstream last-bit noise).
+ * z_old/sdf_old [R, it*N_eval] sorted state of the previous rounds (NULL for it == 0), z_new/sdf_new [R, N_eval] this round's
+ * samples, beta_in/far [R].  Outputs: merged (z, sdf) [R, (it+1)*N_eval] (optional), beta_out [R] after the line search
+ * (:208-220), samples_out = the next round's N_eval samples (:246-307) when the batch-global flag says upsample, else the final
+ * sorted z_vals [R, N + N_extra + 2] (:313-336); *upsample_out_host (HOST int) tells which.  Synchronises the stream. */
+int hold_sampler_round(hold_ctx* ctx, int node, int R, int it, const float* z_old, const float* sdf_old, const float* z_new,
+                       const float* sdf_new, const float* beta_in, const float* far, const float* beta_param,
+                       float* z_merged, float* sdf_merged, float* beta_out, float* samples_out, int32_t* upsample_out_host,
+                       void* stream);
 /* a5+a10+a11+a12: Node.forward after sampling (node.py:55-86): inverse warp, SDF + feature + gradient,
  * forward-skinning Jacobian, normals, colour net, Laplace density.  out->z_vals is an INPUT here. */
 int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_loc, const float* ray_dirs,
@@ -218,12 +229,12 @@ int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, in
 
 /* SURVEY §8f rank 1 — the NeRF++ background (model/renderables/background.py).
  * hold_bg_set_weights: Background.bg_implicit_network (9 plain layers `lin<k>.{weight,bias}`: weight_g NULL) and
- * Background.bg_rendering_network (2 plain layers, 315 -> 128 -> 3).
+ * Background.bg_rendering_network (2 plain layers, 315 -> 128 -> 3); mlp_mode = HOLD_MLP_* arithmetic of both nets.
  * hold_background: HOLDNet.forward's background leg (hold/hold_net.py:91-118,125-134): inverse_sample +
  * Background.forward.  fg_bg_weights [R] is volumetric_render's `bg_weights`; frame_code [B,32] is
  * Background.frame_latent_encoder(idx).  Outputs (any may be NULL): bg_rgb [R,3] (= bg_weights * bg_rgb_only),
  * bg_rgb_only [R,3], bg_semantics [R,4], bg_z_vals [R,32]. */
-int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, void* stream);
+int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, int mlp_mode, void* stream);
 int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const float* ray_dirs, const float* frame_code,
                     const float* fg_bg_weights, float* bg_rgb, float* bg_rgb_only, float* bg_semantics,
                     float* bg_z_vals, void* stream);

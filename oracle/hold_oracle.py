@@ -87,7 +87,7 @@ def density_beta(beta_param, beta_min=1e-4):
 def _error_bound(beta, sdf, dists, d_star):
     """ErrorBoundSampler.get_error_bound, ray_sampler.py:354-366.  sdf [R,n], dists/d_star [R,n-1]."""
     sigma = laplace_density(sdf, beta)
-    fe = torch.cat([torch.zeros(dists.shape[0], 1), dists * sigma[:, :-1]], -1)
+    fe = torch.cat([torch.zeros(dists.shape[0], 1, dtype=dists.dtype), dists * sigma[:, :-1]], -1)
     integral = torch.cumsum(fe, -1)
     eps_sec = torch.exp(-d_star / beta) * dists**2.0 / (4 * beta**2)
     eint = torch.cumsum(eps_sec, -1)
@@ -107,13 +107,86 @@ def _inverse_cdf(cdf, bins, u):
     return b0 + (u - c0) / den * (b1 - b0), inds
 
 
+def sampler_round(z, sdf, beta, beta0, cfg, it, rand=None, final_extras=None):
+    """One iteration of the while loop of ErrorBoundSampler.get_z_vals (ray_sampler.py:160-311) as a pure function of the
+    merged, sorted (z, sdf) [R,n], the per-ray beta [R] entering the round and the round index `it` (0-based).  Works in the
+    dtype of its inputs (float64 inputs give the exact-arithmetic answer the fp32 results are measured against in
+    tests/test_gpu_sampler_rounds.py).  Returns dict(beta, d_star, samples, inds, upsample, not_conv)."""
+    Ne, N = cfg["N_samples_eval"], cfg["N_samples"]
+    eps, add_tiny = cfg["eps"], cfg["add_tiny"]
+    R, dt = z.shape[0], z.dtype
+    beta = beta.clone()
+    dists = z[:, 1:] - z[:, :-1]
+    a, b, c = dists, sdf[:, :-1].abs(), sdf[:, 1:].abs()
+    first = a.pow(2) + b.pow(2) <= c.pow(2)
+    second = a.pow(2) + c.pow(2) <= b.pow(2)
+    d_star = torch.zeros(R, z.shape[1] - 1, dtype=dt)
+    d_star[first] = b[first]
+    d_star[second] = c[second]
+    s = (a + b + c) / 2.0
+    area = s * (s - a) * (s - b) * (s - c)
+    m = ~first & ~second & (b + c - a > 0)
+    d_star[m] = (2.0 * torch.sqrt(area[m])) / a[m]
+    d_star = (sdf[:, 1:].sign() * sdf[:, :-1].sign() == 1) * d_star
+    err = _error_bound(beta0, sdf, dists, d_star)
+    beta[err <= eps] = beta0
+    bmin, bmax = beta0.reshape(1).repeat(R), beta
+    for _ in range(cfg["beta_iters"]):
+        mid = (bmin + bmax) / 2.0
+        err = _error_bound(mid.unsqueeze(-1), sdf, dists, d_star)
+        bmax[err <= eps] = mid[err <= eps]
+        bmin[err > eps] = mid[err > eps]
+    beta = bmax
+    sigma = laplace_density(sdf, beta.unsqueeze(-1))
+    dists1 = torch.cat([dists, torch.full((R, 1), 1e10, dtype=dt)], -1)
+    fe = dists1 * sigma
+    sfe = torch.cat([torch.zeros(R, 1, dtype=dt), fe[:, :-1]], -1)
+    alpha = 1 - torch.exp(-fe)
+    T = torch.exp(-torch.cumsum(sfe, -1))
+    w = alpha * T
+    not_conv = bool(beta.max() > beta0)
+    upsample = not_conv and (it + 1) < cfg["max_total_iters"]
+    if upsample:
+        n_new = Ne
+        eps_sec = torch.exp(-d_star / beta.unsqueeze(-1)) * dists**2.0 / (4 * beta.unsqueeze(-1) ** 2)
+        eint = torch.cumsum(eps_sec, -1)
+        pdf = (torch.clamp(torch.exp(eint), max=1.0e6) - 1.0) * T[:, :-1] + add_tiny
+    else:
+        n_new = N
+        pdf = w[:, :-1] + 1e-5
+    pdf = pdf / pdf.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros(R, 1, dtype=dt), torch.cumsum(pdf, -1)], -1)
+    if upsample or rand is None:
+        u = torch.linspace(0.0, 1.0, steps=n_new, dtype=dt).unsqueeze(0).repeat(R, 1)
+    else:
+        u = rand["u"]
+    samples, inds = _inverse_cdf(cdf, z, u.contiguous())
+    return dict(beta=beta, d_star=d_star, samples=samples, inds=inds, upsample=upsample, not_conv=not_conv)
+
+
+def final_z_vals(samples, z, far, cfg, rand=None):
+    """ray_sampler.py:313-336: the N weight-CDF samples + near + far + N_extra strided (eval) entries of z, sorted."""
+    Nx, R = cfg["N_samples_extra"], samples.shape[0]
+    near = torch.full((R, 1), float(cfg["near"]), dtype=samples.dtype)
+    if Nx > 0:
+        if rand is None:
+            eidx = torch.linspace(0, z.shape[1] - 1, Nx).long()
+        else:
+            eidx = rand["extra_idx"]
+        extra = torch.cat([near, far, z[:, eidx]], -1)
+    else:
+        extra = torch.cat([near, far], -1)
+    zf, _ = torch.sort(torch.cat([samples, extra], -1), -1)
+    return zf
+
+
 def error_bound_sample(sdf_query, dirs, cam, beta0, cfg, bounding_sphere, rand=None, trace=None):
     """ErrorBoundSampler.get_z_vals with inverse_sphere_bg=True, ray_sampler.py:128-352
     (VolSDF Algorithm 1).  sdf_query(points[P,3]) -> sdf[P] is `sdf_func_with_deformer(...)[0]`.
     rand: None for eval (deterministic linspace u / extras) or dict(jitter[R,Ne], u[R,N], extra_idx[Nx]).
     Returns z_vals [R, N + N_extra + 2] and the number of rounds run (batch-global, :244)."""
-    Ne, N, Nx = cfg["N_samples_eval"], cfg["N_samples"], cfg["N_samples_extra"]
-    eps, add_tiny = cfg["eps"], cfg["add_tiny"]
+    Ne = cfg["N_samples_eval"]
+    eps = cfg["eps"]
     R = dirs.shape[0]
     far = sphere_far(cam, dirs, bounding_sphere)
     z = uniform_z(cfg["near"], far, Ne, None if rand is None else rand["jitter"])
@@ -124,72 +197,21 @@ def error_bound_sample(sdf_query, dirs, cam, beta0, cfg, bounding_sphere, rand=N
     while not_conv and it < cfg["max_total_iters"]:
         pts = cam.unsqueeze(1) + samples.unsqueeze(2) * dirs.unsqueeze(1)
         s_new = sdf_query(pts.reshape(-1, 3)).reshape(R, -1)
+        z_in, s_in, beta_in = samples.clone(), s_new.clone(), beta.clone()   # trace only: this round's inputs
         if idx is not None:
             sdf = torch.gather(torch.cat([sdf, s_new], -1), 1, idx)
         else:
             sdf = s_new
-        dists = z[:, 1:] - z[:, :-1]
-        a, b, c = dists, sdf[:, :-1].abs(), sdf[:, 1:].abs()
-        first = a.pow(2) + b.pow(2) <= c.pow(2)
-        second = a.pow(2) + c.pow(2) <= b.pow(2)
-        d_star = torch.zeros(R, z.shape[1] - 1)
-        d_star[first] = b[first]
-        d_star[second] = c[second]
-        s = (a + b + c) / 2.0
-        area = s * (s - a) * (s - b) * (s - c)
-        m = ~first & ~second & (b + c - a > 0)
-        d_star[m] = (2.0 * torch.sqrt(area[m])) / a[m]
-        d_star = (sdf[:, 1:].sign() * sdf[:, :-1].sign() == 1) * d_star
-        err = _error_bound(beta0, sdf, dists, d_star)
-        beta[err <= eps] = beta0
-        bmin, bmax = beta0.reshape(1).repeat(R), beta
-        for _ in range(cfg["beta_iters"]):
-            mid = (bmin + bmax) / 2.0
-            err = _error_bound(mid.unsqueeze(-1), sdf, dists, d_star)
-            bmax[err <= eps] = mid[err <= eps]
-            bmin[err > eps] = mid[err > eps]
-        beta = bmax
-        sigma = laplace_density(sdf, beta.unsqueeze(-1))
-        dists1 = torch.cat([dists, torch.full((R, 1), 1e10)], -1)
-        fe = dists1 * sigma
-        sfe = torch.cat([torch.zeros(R, 1), fe[:, :-1]], -1)
-        alpha = 1 - torch.exp(-fe)
-        T = torch.exp(-torch.cumsum(sfe, -1))
-        w = alpha * T
+        rd = sampler_round(z, sdf, beta, beta0, cfg, it, rand)
+        beta, samples, not_conv, upsample = rd["beta"], rd["samples"], rd["not_conv"], rd["upsample"]
         it += 1
-        not_conv = bool(beta.max() > beta0)
-        upsample = not_conv and it < cfg["max_total_iters"]
-        if upsample:
-            n_new = Ne
-            eps_sec = torch.exp(-d_star / beta.unsqueeze(-1)) * dists**2.0 / (4 * beta.unsqueeze(-1) ** 2)
-            eint = torch.cumsum(eps_sec, -1)
-            pdf = (torch.clamp(torch.exp(eint), max=1.0e6) - 1.0) * T[:, :-1] + add_tiny
-        else:
-            n_new = N
-            pdf = w[:, :-1] + 1e-5
-        pdf = pdf / pdf.sum(-1, keepdim=True)
-        cdf = torch.cat([torch.zeros(R, 1), torch.cumsum(pdf, -1)], -1)
-        if upsample or rand is None:
-            u = torch.linspace(0.0, 1.0, steps=n_new).unsqueeze(0).repeat(R, 1)
-        else:
-            u = rand["u"]
-        samples, inds = _inverse_cdf(cdf, z, u.contiguous())
         if trace is not None:
-            trace.append(dict(it=it, z=z.clone(), sdf=sdf.clone(), beta=beta.clone(), d_star=d_star.clone(),
-                              samples=samples.clone(), inds=inds.clone(), upsample=upsample))
+            trace.append(dict(it=it, z=z.clone(), sdf=sdf.clone(), beta=beta.clone(), d_star=rd["d_star"].clone(),
+                              samples=samples.clone(), inds=rd["inds"].clone(), upsample=upsample,
+                              z_in=z_in, s_in=s_in, beta_in=beta_in, far=far.clone()))
         if upsample:
             z, idx = torch.sort(torch.cat([z, samples], -1), -1)
-    near = torch.full((R, 1), float(cfg["near"]))
-    if Nx > 0:
-        if rand is None:
-            eidx = torch.linspace(0, z.shape[1] - 1, Nx).long()
-        else:
-            eidx = rand["extra_idx"]
-        extra = torch.cat([near, far, z[:, eidx]], -1)
-    else:
-        extra = torch.cat([near, far], -1)
-    zf, _ = torch.sort(torch.cat([samples, extra], -1), -1)
-    return zf, it
+    return final_z_vals(samples, z, far, cfg, rand), it
 
 
 # ----------------------------------------------------------------------------- a8/a9/a11: embedder + MLPs

@@ -25,7 +25,7 @@ def test_header_symbols_exported(built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hold_b200.h but not exported"
     assert set(names) == set(capi.EXPORTS), "ctypes table and header disagree"
-    assert lib.hold_version() == 100
+    assert lib.hold_version() == 200
 
 
 def test_struct_layouts_match_header(built):

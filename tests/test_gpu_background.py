@@ -6,7 +6,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_background_and_full_composite(ctx):
+BG_TOL = {"fp32": 1e-5, "tc": 1e-4}   # colours in [0,1]: 1e-4 is the north-star bar; the exact-fp32 path holds 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_background_and_full_composite(ctx, mode):
     from hold_b200 import capi, scene_io, synth
     from hold_b200.model import HOLDNet
     from oracle import hold_oracle as O
@@ -15,8 +19,9 @@ def test_background_and_full_composite(ctx):
     sc.intrinsics[:, 0, 2] += 0.37   # keep every ray off the sphere centre (0/0 in the reference's depth2pts_outside)
     sc.intrinsics[:, 1, 2] -= 0.21
     dev = torch.device("cuda", 0)
-    net = scene_io.build_net(sc, ctx, capi.MLP_FP32)
-    bg, sdf_sd, rgb_sd = scene_io.build_background(sc, ctx)
+    mm = capi.MLP_TC if mode == "tc" else capi.MLP_FP32
+    net = scene_io.build_net(sc, ctx, mm)
+    bg, sdf_sd, rgb_sd = scene_io.build_background(sc, ctx, mlp_mode=mm)
     full = HOLDNet(ctx, dict(net.nodes), background=bg)
     out = full(scene_io.scene_input(sc, dev))
     ctx.check()
@@ -33,8 +38,8 @@ def test_background_and_full_composite(ctx):
     for name, a, b in (("bg_rgb", out["rgb"].cpu() - out["fg_rgb"].cpu(), o[0]), ("bg_rgb_only", out["bg_rgb_only"].cpu(), o[1]),
                        ("bg_z_vals", out["bg_z_vals"].cpu(), o[3])):
         err = (a - b).abs().max().item()
-        print(f"{name}: max|d| {err:.2e}")
-        assert err <= 1e-5, f"{name}: max|d| {err:.2e}"
+        print(f"[{mode}] {name}: max|d| {err:.2e}")
+        assert err <= BG_TOL[mode], f"{name}: max|d| {err:.2e}"
     sem = out["semantics"].cpu() - out["fg_semantics"].cpu()
     assert (sem - o[2]).abs().max().item() <= 1e-6
     assert out["instance_map"].shape == (sc.B * P,) and out["instance_map"].dtype == torch.int64
@@ -46,7 +51,8 @@ def test_background_and_full_composite(ctx):
     assert d.mean().item() <= 8e-3 and d.max().item() <= 1.5e-1
 
 
-def test_background_against_reference_golden(ctx):
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_background_against_reference_golden(ctx, mode):
     """hold_background against the committed outputs of the reference's own Background class."""
     import os
     from hold_b200 import capi, synth
@@ -62,7 +68,7 @@ def test_background_against_reference_golden(ctx):
     sdf_sd, rgb_sd = synth.make_bg_state(i["bg_state_seed"])
     wi, k1 = capi.mlp_weights({k: v.to(dev) for k, v in sdf_sd.items()}, 9)
     wr, k2 = capi.mlp_weights({k: v.to(dev) for k, v in rgb_sd.items()}, 2)
-    check(lib().hold_bg_set_weights(ctx.h, C.byref(wi), C.byref(wr), stream_ptr()))
+    check(lib().hold_bg_set_weights(ctx.h, C.byref(wi), C.byref(wr), capi.MLP_TC if mode == "tc" else capi.MLP_FP32, stream_ptr()))
     R = i["ray_dirs"].shape[0]
     t = {k: i[k].to(dev).float().contiguous() for k in ("cam_loc", "ray_dirs", "frame_code", "bg_weights")}
     out = dict(bg_rgb=torch.empty(R, 3, device=dev), bg_rgb_only=torch.empty(R, 3, device=dev),
@@ -72,42 +78,5 @@ def test_background_against_reference_golden(ctx):
     ctx.check()
     for k, v in out.items():
         err = (v.cpu() - ref[k]).abs().max().item()
-        assert err <= 1e-5, f"{k}: {err:.2e}"
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HOLD_RUN_VARIANTS") != "1", reason="opt-in: HOLD_RUN_VARIANTS=1 (tcgen05 code without a hardware run)")
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")
-def test_background_tcgen05_variant_matches_fp32(ctx):
-    """HOLD_BG_TC=1: the background nets on the tensor-core kernels against the exact-fp32 path (same inputs)."""
-    import os
-    import subprocess
-    import sys
-
-    code = """
-import torch, ctypes as C
-from hold_b200 import capi, scene_io, synth
-from hold_b200.capi import check, lib, ptr, stream_ptr
-ctx = capi.Context(0); dev = torch.device("cuda", 0)
-sc = synth.make_scene(H=10, W=10, S=32, B=2, seed=8)
-sc.intrinsics[:, 0, 2] += 0.37; sc.intrinsics[:, 1, 2] -= 0.21
-scene_io.build_net(sc, ctx, capi.MLP_FP32)
-bg, _, _ = scene_io.build_background(sc, ctx)
-from oracle import hold_oracle as O
-dirs, cam = O.camera_rays(sc.uv, sc.extrinsics, sc.intrinsics)
-P = dirs.shape[1]
-dirs, cam = dirs.reshape(-1, 3).to(dev), cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3).to(dev)
-out = bg(torch.rand(dirs.shape[0], generator=torch.Generator().manual_seed(0)).to(dev), dirs, cam, sc.frame_idx.to(dev), 2)
-ctx.check()
-torch.save({k: v.cpu() for k, v in out.items()}, OUT)
-"""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = {}
-    for flag in ("0", "1"):
-        path = os.path.join(root, "tests", "_build", f"bg_tc_{flag}.pt")
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        env = dict(os.environ, HOLD_BG_TC=flag, PYTHONPATH=root)
-        subprocess.run([sys.executable, "-c", code.replace("OUT", repr(path))], check=True, env=env, cwd=root, timeout=300)
-        res[flag] = torch.load(path)
-    for k in ("bg_rgb", "bg_rgb_only"):
-        err = (res["1"][k] - res["0"][k]).abs().max().item()
-        assert err < 2e-4, f"{k}: {err:.2e}"
+        print(f"[{mode}] {k}: {err:.2e}")
+        assert err <= BG_TOL[mode], f"{k}: {err:.2e}"

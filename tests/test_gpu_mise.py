@@ -1,6 +1,6 @@
 """the GPU MISE + fused-MLP SDF queries against the reference's own compiled MISE (oracle/_ref, travels
 with the snapshot) fed with the SAME SDF values round by round -> identical dense grids.  The restatement itself is already
-checked bit for bit on the CPU (tests/test_cpu_mise.py); no hardware run yet, hence non-strict xfail."""
+checked bit for bit on the CPU (tests/test_cpu_mise.py); green on hardware since round 1, strict since round 2."""
 import glob
 import os
 import sys
@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

@@ -1,11 +1,11 @@
 """the pose servers under autograd (optimize_ckpt.py's `server.forward_param` + backward).
 hold_mano_lbs_bwd / hold_object_tf_bwd against torch.autograd over the oracle (pinned to the reference's own autograd in
 oracle/ref_harness.py check_pose_grads).  The kernels' phase code is already exercised on the CPU
-(tests/test_cpu_pose_bwd.py); these cases had no hardware run yet when they were written, hence non-strict xfail."""
+(tests/test_cpu_pose_bwd.py); green on hardware since round 1, strict since round 2."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def impl_mano_server_backward(ctx):
