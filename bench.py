@@ -96,44 +96,103 @@ def make_scene(seed=0, H_=H, W_=W):
     return sc
 
 
-def cpu_reference_rays_per_s(n_rays: int, repeats: int = 1, threads: int | None = None):
-    """The reference's algorithm (oracle port, pinned to the reference modules by oracle/ref_harness.py) on the
-    host cores, in the reference's own 512-ray chunks (datasets/eval_datasets.py:13)."""
+def _cpu_worker(rank, n_workers, threads, n_rays, repeats, barrier, q):
+    """One worker of the CPU arm: its own disjoint 512-ray chunks of the frame, `threads` torch threads."""
+    import torch as th
+
+    th.set_num_threads(threads)
+    sys.path.insert(0, ROOT)
     from oracle import hold_oracle as O
 
-    # Thread sweep on the round-1 GPU box (2 x Xeon 8562Y+, 128 hw threads), same workload: 16 threads 105 rays/s,
-    # 32: 89, 64: 56, 128: 0.84 (oversubscribed tiny GEMMs).  The baseline uses the best setting, not the most threads.
-    threads = threads or int(os.environ.get("HOLD_CPU_THREADS", min(16, os.cpu_count() or 1)))
-    torch.set_num_threads(threads)
     sc2 = make_scene(0)
-    g = torch.Generator().manual_seed(11)
-    ids = torch.sort(torch.randperm(H * W, generator=g)[:n_rays]).values
-    O.render_scene(sc2, ray_ids=ids[:64], chunk=64)  # warm-up
+    g = th.Generator().manual_seed(11)
+    ids_all = th.randperm(H * W, generator=g)[: n_rays * n_workers]
+    ids = th.sort(ids_all[rank * n_rays:(rank + 1) * n_rays]).values
+    O.render_scene(sc2, ray_ids=ids[:64], chunk=64)  # warm-up (allocator, thread pool)
+    barrier.wait()
     t0 = time.perf_counter()
     for _ in range(repeats):
         O.render_scene(sc2, ray_ids=ids, chunk=512)
+    q.put((rank, time.perf_counter() - t0))
+
+
+def cpu_reference_rays_per_s(n_rays_per_worker: int = 1024, repeats: int = 1, threads: int | None = None, workers: int | None = None):
+    """The reference's algorithm (oracle port, pinned to the reference modules by oracle/ref_harness.py) on ALL host cores:
+    rays are independent, so the frame's 512-ray chunks (datasets/eval_datasets.py:13) are farmed over `workers` processes of
+    `threads` torch threads each (one process tops out at ~16 threads on these small GEMMs: sweep on the round-1 box, 2 x Xeon
+    8562Y+: 16 threads 105 rays/s, 32: 89, 64: 56, 128: 0.84).  Wall clock from a common start barrier to the last worker's end."""
+    import multiprocessing as mp
+
+    ncpu = os.cpu_count() or 1
+    threads = threads or int(os.environ.get("HOLD_CPU_THREADS", min(16, ncpu)))
+    workers = workers or int(os.environ.get("HOLD_CPU_WORKERS", max(1, ncpu // threads)))
+    ctx = mp.get_context("spawn")
+    barrier, q = ctx.Barrier(workers + 1), ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, workers, threads, n_rays_per_worker, repeats, barrier, q)) for r in range(workers)]
+    for p_ in procs:
+        p_.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    done = [q.get() for _ in procs]
     dt = time.perf_counter() - t0
-    return n_rays * repeats / dt, threads, dt
+    for p_ in procs:
+        p_.join()
+    total = n_rays_per_worker * workers * repeats
+    return total / dt, threads * workers, dt, dict(workers=workers, threads_per_worker=threads, rays=total,
+                                                    slowest_worker_s=max(d for _, d in done))
+
+
+def _cpu_line(rps, cores, dt, info, steps):
+    return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{info['rays']} rays of the same 512x512 workload ({info['workers']} processes x {info['threads_per_worker']} threads, "
+                      f"disjoint 512-ray chunks, {steps} pass(es)) in {dt:.1f} s wall; oracle/hold_oracle.py = torch-CPU fp32 restatement pinned "
+                      f"to the reference's own modules (oracle/ref_harness.py; /root/reference cannot travel to the GPU box, hence 'port')"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = 2048
-    rps, threads, dt = cpu_reference_rays_per_s(n_rays, repeats=max(1, args.steps))
+    reps = max(1, args.steps)
+    # one 512-ray chunk per worker and step: ~5 s per step on the GPU box's host, so that --steps 20 ends within a few minutes
+    rps, cores, dt, info = cpu_reference_rays_per_s(512, repeats=reps)
     line = {
         "impl": "reference", "metric": "rays/sec (128 samples/ray)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / reps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: right hand + rigid object, 512x512 frame, 128 samples/ray (N_eval 128, N 64, extra 32), beta 0.03 -> 5 sampler rounds",
-                   "sample": f"{n_rays} rays of the frame per step, 512-ray chunks"},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_rays} rays x {max(1, args.steps)} steps of the 512x512 workload, torch CPU fp32, {threads} threads (best of a 16/32/64/128 sweep)"},
+                   "sample": f"{info['rays'] // reps} rays of the frame per step, 512-ray chunks over {info['workers']} processes x {info['threads_per_worker']} threads"},
+        "cpu_baseline": _cpu_line(rps, cores, dt, info, reps),
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the newest committed ncu --set full capture
+    (profiles/r*_ncu_k_mlp_tc0*_raw.csv), or None."""
+    import csv
+    import glob
+
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_mlp_tc0*raw.csv")))
+    for path in reversed(cands):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            for r in rows[2:]:
+                d = dict(zip(hdr, r))
+                if "k_mlp_tc" not in d.get("Kernel Name", ""):
+                    continue
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    u = units[hdr.index(k)].lower()
+                    mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+                    tot += float(d[k]) * mult
+                return tot, os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
 
 
 def main():
@@ -254,11 +313,11 @@ def main():
     k_flops = 2.0 * MAC_SDF_HEAD * P
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     passes = 3 if use_tc else 1
-    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-    # (profiles/r01_ncu_k_mlp_tc0.md): 414.1 MB + 119.1 MB = the algorithmic 403 MB of x_c in + 134 MB of sdf out.
-    traffic_bytes = 533.2e6 if use_tc else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, read from the committed ncu --set full capture
+    traffic_bytes, traffic_src = ncu_traffic_bytes() if use_tc else (None, None)
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic_bytes,
+        "bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic_bytes, "traffic_source": traffic_src,
+        "algorithmic_bytes": 16.0 * P,
         "kernel": "SDF-net launch of one sampler round (262144 x 128 points, sdf head only: 0.918 MFLOP/point algorithmic)",
         "ms_per_launch": k_ms, "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({how}, burst: kernel timed alone)",
         "mma_mode": "tcgen05 kind::f16, fp16 hi/lo split x3 passes (fp32-level operands, fp32 accumulate)" if use_tc else "fp32 FFMA on CUDA cores (no tensor pipe)",
@@ -273,10 +332,8 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rps, threads, dt = cpu_reference_rays_per_s(2048, repeats=1)
-        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"2048 rays (four reference-sized 512-ray chunks) of the same 512x512 workload in {dt:.1f} s; oracle/hold_oracle.py "
-                         f"(torch CPU fp32, {threads} threads = best of a 16/32/64/128 sweep on this host type)"}
+        rps, cores, dt, info = cpu_reference_rays_per_s(1024, repeats=1)
+        cpu = _cpu_line(rps, cores, dt, info, 1)
     line = {
         "metric": "rays/sec (128 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -11,8 +11,11 @@ that carries learnable state on the hot path, so loading is a prefix strip plus 
     model.nodes.object.frame_latent_encoder.weight                         -> Node.frame_latent_encoder
     model.background.{bg_implicit_network,bg_rendering_network}.lin<k>.*, .frame_latent_encoder.weight -> Background
 
-Ignored on purpose: server / deformer / object_model buffers (`v3d_cano`, `norm_mat`, MANO tensors: given to the mirror's
-constructors), the BARF embedder counters (`embedder_obj.alpha_*`: eval() uses all-ones weights, render.py:43-47)."""
+    model.nodes.object.server.object_model.{obj_scale,norm_mat,v3d_cano}   -> ObjectServer.set_object_model (denorm_mat is
+                                                                               rebuilt from norm_mat, object_model.py:27)
+
+Ignored on purpose: the MANO server / deformer tensors (given to the mirror's constructors), the BARF embedder counters
+(`embedder_obj.alpha_*`: eval() uses all-ones weights, render.py:43-47)."""
 from __future__ import annotations
 
 import torch
@@ -41,6 +44,21 @@ class GenericParams(nn.Module):
             ids = torch.zeros_like(frame_ids) if name == "betas" else frame_ids
             out[f"{self.node_id}.{name}"] = getattr(self, name)(ids)
         return out
+
+
+OBJECT_MODEL_KEYS = ("obj_scale", "norm_mat", "v3d_cano")
+
+
+def object_model_buffers(sd: dict, prefix: str = "model.") -> dict:
+    """{node_id: {obj_scale, norm_mat, v3d_cano}} found under `<prefix>nodes.<id>.server.object_model.*`."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith(prefix + "nodes.") and ".server.object_model." in k:
+            nid = k[len(prefix) + len("nodes."):].split(".", 1)[0]
+            name = k.rsplit(".", 1)[1]
+            if name in OBJECT_MODEL_KEYS:
+                out.setdefault(nid, {})[name] = v
+    return out
 
 
 def split_reference_state_dict(sd: dict, prefix: str = "model."):
@@ -78,6 +96,16 @@ def load_reference_state_dict(net, sd: dict, prefix: str = "model.", strict: boo
                 loaded += 1
             else:
                 missing.append(f"nodes.{nid}.{k}")
+    # ObjectModel buffers: not parameters of the mirror, but they decide the object's transform (obj_tfs, verts)
+    for nid, bufs in object_model_buffers(sd, prefix).items():
+        node = net.nodes[nid] if nid in net.nodes else None
+        if node is None or not hasattr(node.server, "set_object_model"):
+            continue
+        if "v3d_cano" in bufs and tuple(bufs["v3d_cano"].shape) != tuple(node.server.v3d_cano.shape) and strict:
+            raise KeyError(f"nodes.{nid}.server.object_model.v3d_cano is {tuple(bufs['v3d_cano'].shape)}, the mirror holds "
+                           f"{tuple(node.server.v3d_cano.shape)}")
+        node.server.set_object_model(obj_scale=bufs.get("obj_scale"), norm_mat=bufs.get("norm_mat"), v3d_cano=bufs.get("v3d_cano"))
+        loaded += len(bufs)
     if getattr(net, "background", None) is not None:
         own = net.background.state_dict()
         for k, t in own.items():

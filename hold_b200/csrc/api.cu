@@ -65,6 +65,7 @@ static int check_node(hold_ctx* ctx, int node, bool need_weights) {
   HOLD_REQUIRE(node >= 0 && node < HOLD_MAX_NODES, "node %d out of range", node);
   if (!ctx->nodes[node].configured) { set_error("node %d not configured", node); return HOLD_E_STATE; }
   if (need_weights && !ctx->nodes[node].has_weights) { set_error("node %d has no weights", node); return HOLD_E_STATE; }
+  HOLD_CUDA(cudaSetDevice(ctx->device));   // launches go to the context's device whatever the caller's current device is
   return HOLD_OK;
 }
 
@@ -133,10 +134,7 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
     // hot path: consecutive samples of a ray per thread, KNN seeded from the previous sample
     const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
     dim3 g2(ceil_div(rays * segs, 128), B);
-    const bool knn_occ = ctx->knn_variant == 2, knn_filt = ctx->knn_variant == 1;   // hold_debug_set(ctx, 1, v): A/B only
-    if (knn_filt) k_inverse_warp_hand_rays_filt<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
-    else if (knn_occ) k_inverse_warp_hand_rays_occ<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
-    else k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, xc, st);
+    k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, ns.knn_perm, xc, st);
     HOLD_LAUNCH_CHECK(ctx);
     return HOLD_OK;
   }
@@ -217,6 +215,7 @@ int hold_ctx_destroy(hold_ctx* ctx) {
     for (float* p : ptrs)
       if (p) cudaFree(p);
     if (ns.sstate) cudaFree(ns.sstate);
+    if (ns.knn_perm) cudaFree(ns.knn_perm);
     tc_free(ns);
   }
   tc_bg_free(ctx->bg_tc);
@@ -365,6 +364,23 @@ int hold_node_set_rig(hold_ctx* ctx, int node, const float* cano_verts, const fl
   if (rc) return rc;
   HOLD_CUDA(cudaMemcpyAsync(ns.cano_verts, cano_verts, kVerts * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   HOLD_CUDA(cudaMemcpyAsync(ns.skin_w, skin_weights, kVerts * kJoints * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  {  // vertex groups of the cluster-pruned KNN (knn_phases.h): ordered once on the canonical hand, on the host
+    static_assert(knnc::kNV == kVerts && knnc::kK == kKnn, "knn_phases.h constants");
+    float* hv = (float*)malloc(sizeof(float) * kVerts * (3 + kJoints));
+    HOLD_REQUIRE(hv != nullptr, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(hv, ns.cano_verts, kVerts * 3 * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hv + kVerts * 3, ns.skin_w, kVerts * kJoints * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    unsigned short perm[knnc::kNCl * knnc::kClSize];
+    if (e == cudaSuccess) {
+      knnc::cluster_order(hv, hv + kVerts * 3, kJoints, perm);
+      if (!ns.knn_perm) e = cudaMalloc((void**)&ns.knn_perm, sizeof(perm));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ns.knn_perm, perm, sizeof(perm), cudaMemcpyHostToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // `perm` is a stack buffer
+    }
+    free(hv);
+    if (e != cudaSuccess) { set_error("hold_node_set_rig: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
+  }
   ns.has_rig = true;
   return HOLD_OK;
 }
@@ -373,6 +389,7 @@ int hold_mano_lbs(hold_ctx* ctx, const hold_mano_model* m, int B, const float* b
                   const float* transl, const float* scene_scale, const float* tfs_c_inv, float* verts, float* jnts,
                   float* tfs, float* v_posed, void* stream) {
   HOLD_REQUIRE(ctx && m, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return HOLD_OK;
   HOLD_REQUIRE(betas && full_pose && transl && scene_scale && verts && jnts && tfs && v_posed, "NULL tensor");
@@ -400,6 +417,7 @@ int hold_mano_lbs_bwd(hold_ctx* ctx, const hold_mano_model* m, int B, const floa
                       const float* g_jnts, const float* g_tfs, float* g_betas, float* g_pose, float* g_transl, float* g_scale,
                       void* stream) {
   HOLD_REQUIRE(ctx && m, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return HOLD_OK;
   HOLD_REQUIRE(betas && full_pose && transl && scene_scale && g_betas && g_pose && g_transl && g_scale, "NULL tensor");
@@ -427,6 +445,7 @@ int hold_object_tf_bwd(hold_ctx* ctx, int B, const float* rot, const float* tran
                        const float* denorm_mat, const float* pts_cano, int Nv, const float* g_verts, const float* g_tfs,
                        float* g_rot, float* g_trans, float* g_scene_scale, float* g_obj_scale, void* stream) {
   HOLD_REQUIRE(ctx && rot && trans && scene_scale && denorm_mat && g_rot && g_trans && g_scene_scale && g_obj_scale, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   if (B <= 0) return HOLD_OK;
   HOLD_REQUIRE(g_verts == nullptr || (pts_cano != nullptr && Nv > 0), "g_verts given without canonical points");
   const int nt = 256, smem = posebwd::obj_scratch_floats(nt) * (int)sizeof(float);
@@ -439,6 +458,7 @@ int hold_object_tf_bwd(hold_ctx* ctx, int B, const float* rot, const float* tran
 int hold_object_tf(hold_ctx* ctx, int B, const float* rot, const float* trans, const float* scene_scale, float obj_scale,
                    const float* denorm_mat, const float* pts_cano, int Nv, float* tfs, float* verts, void* stream) {
   HOLD_REQUIRE(ctx && rot && trans && scene_scale && denorm_mat && tfs, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   if (B <= 0) return HOLD_OK;
   HOLD_REQUIRE(verts == nullptr || (pts_cano != nullptr && Nv > 0), "verts requested without canonical points");
   dim3 grid(verts ? max(1, min(ceil_div(Nv, 128), 64)) : 1, B);
@@ -450,6 +470,7 @@ int hold_object_tf(hold_ctx* ctx, int B, const float* rot, const float* trans, c
 int hold_camera_rays(hold_ctx* ctx, int B, int P, const float* uv, const float* pose, const float* intrinsics,
                      float* ray_dirs, float* cam_loc, void* stream) {
   HOLD_REQUIRE(ctx && uv && pose && intrinsics && ray_dirs && cam_loc, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   if (B * P <= 0) return HOLD_OK;
   k_camera_rays<<<ceil_div(B * P, 256), 256, 0, (cudaStream_t)stream>>>(B, P, uv, pose, intrinsics, ray_dirs, cam_loc);
   HOLD_LAUNCH_CHECK(ctx);
@@ -644,6 +665,7 @@ int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_lo
 int hold_composite(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors, const int32_t* class_ids_host,
                    const hold_render_out* comp, const hold_render_out* per_node, void* stream) {
   HOLD_REQUIRE(ctx && factors && class_ids_host, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(n >= 1 && n <= HOLD_MAX_NODES, "n = %d out of [1,%d]", n, HOLD_MAX_NODES);
   HOLD_REQUIRE(R >= 0 && S >= 2, "bad R/S");
   if (R == 0) return HOLD_OK;
@@ -710,6 +732,7 @@ int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, in
 int hold_mesh_sdf(hold_ctx* ctx, int B, int P, const float* points, int V, const float* verts, int verts_batched, int F,
                   const int32_t* faces, float* sdf, int32_t* face_idx, void* stream) {
   HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(B >= 0 && P >= 0 && V > 0 && F > 0, "bad sizes");
   if (B == 0 || P == 0) return HOLD_OK;
   HOLD_REQUIRE(points && verts && faces && sdf, "NULL argument");
@@ -722,6 +745,7 @@ int hold_mesh_sdf(hold_ctx* ctx, int B, int P, const float* points, int V, const
 int hold_off_in_surface(hold_ctx* ctx, int R, int S, const float* sdf, float threshold, uint8_t* off_surface,
                         uint8_t* in_surface, void* stream) {
   HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(R >= 0 && S >= 1, "bad sizes");
   if (R == 0) return HOLD_OK;
   HOLD_REQUIRE(sdf != nullptr, "NULL argument");
@@ -769,6 +793,7 @@ int hold_mise_destroy(hold_mise* h) {
 
 int hold_mise_create(hold_ctx* ctx, int resolution_0, int depth, float threshold, hold_mise** out, void* stream) {
   HOLD_REQUIRE(ctx && out, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   HOLD_REQUIRE(resolution_0 >= 1 && depth >= 0 && depth <= mise::kMaxDepth, "bad MISE shape");
   HOLD_REQUIRE(((long long)resolution_0 << depth) <= 1024, "MISE resolution above 1024 is not supported");
   hold_mise* h = new (std::nothrow) hold_mise();
@@ -805,6 +830,7 @@ int hold_mise_create(hold_ctx* ctx, int resolution_0, int depth, float threshold
 
 int hold_mise_query(hold_mise* h, int32_t* coords, int capacity, int* n_points, void* stream) {
   HOLD_REQUIRE(h && n_points, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(h->ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   HOLD_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), s));
   k_mise_collect<<<h->ctx->sm_count * 8, 256, 0, s>>>(h->g, h->queue, h->counter, (unsigned int)h->np);
@@ -823,6 +849,7 @@ int hold_mise_query(hold_mise* h, int32_t* coords, int capacity, int* n_points, 
 
 int hold_mise_update(hold_mise* h, const float* values, int n_values, void* stream) {
   HOLD_REQUIRE(h && (values || n_values == 0), "NULL argument");
+  HOLD_CUDA(cudaSetDevice(h->ctx->device));
   HOLD_REQUIRE(n_values == h->n_last, "update with %d values after a query of %d points", n_values, h->n_last);
   cudaStream_t s = (cudaStream_t)stream;
   if (n_values > 0) {
@@ -847,6 +874,7 @@ int hold_mise_update(hold_mise* h, const float* values, int n_values, void* stre
 
 int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
   HOLD_REQUIRE(h && out, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(h->ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   k_mise_dense_init<<<h->ctx->sm_count * 8, 256, 0, s>>>(h->g, out);
   HOLD_LAUNCH_CHECK(h->ctx);
@@ -857,11 +885,10 @@ int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
   return HOLD_OK;
 }
 
-/* debug/test hook (not in the public header): 1 = hand KNN kernel variant for A/B runs (0 default, 1 filtered scan, 2 occupancy) */
+/* measurement hook (not in the public header): key 2 = accumulator compensation c of the tcgen05 SDF chains (profiles/r02_tc_accumulator_bias.md) */
 int hold_debug_set(hold_ctx* ctx, int key, int value) {
   if (!ctx) return HOLD_E_BADARG;
-  if (key == 1) ctx->knn_variant = value;
-  else if (key == 2) ctx->tc_acc_comp = value;
+  if (key == 2) ctx->tc_acc_comp = value;
   else return HOLD_E_BADARG;
   return HOLD_OK;
 }
@@ -876,6 +903,7 @@ int hold_debug_ws_copy(hold_ctx* ctx, int slot, void* dst, size_t bytes) {
 
 int hold_bg_set_weights(hold_ctx* ctx, const hold_mlp_weights* sdf, const hold_mlp_weights* rgb, int mlp_mode, void* stream) {
   HOLD_REQUIRE(ctx && sdf && rgb, "NULL argument");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   HOLD_REQUIRE(sdf->n_layers == 9 && rgb->n_layers == 2, "background nets: 9 + 2 layers expected");
   HOLD_REQUIRE(sdf->in_dim[0] == kBgEmbed + kBgFrame, "bg lin0 in_dim %d, expected 116", sdf->in_dim[0]);
@@ -923,6 +951,7 @@ int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const flo
                     const float* fg_bg_weights, float* bg_rgb, float* bg_rgb_only, float* bg_semantics, float* bg_z_vals,
                     void* stream) {
   HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->has_bg) { set_error("background weights not set (hold_bg_set_weights)"); return HOLD_E_STATE; }
   HOLD_REQUIRE(R >= 0 && B >= 1, "bad R/B");
   if (R == 0) return HOLD_OK;
@@ -982,6 +1011,52 @@ int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c, const float*
   HOLD_REQUIRE(x_c && sdf, "NULL argument");
   HOLD_REQUIRE((grad == nullptr) == (feat == nullptr), "grad and feat must be requested together");
   return launch_sdf(ctx, ctx->nodes[node], P, x_c, embed_w, sdf, grad, feat, nullptr, (cudaStream_t)stream);
+}
+
+int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const float* normals, const float* pose_cond,
+                  const float* feat, const float* time_code, float* rgb, void* stream) {
+  int rc = check_node(ctx, node, true);
+  if (rc) return rc;
+  HOLD_REQUIRE(B >= 1 && P >= 0, "bad sizes");
+  if (P == 0) return HOLD_OK;
+  HOLD_REQUIRE(P % B == 0, "P (%d) must be B (%d) frames x points, frame-major", P, B);
+  HOLD_REQUIRE(x_c && normals && feat && rgb, "NULL argument");
+  NodeState& ns = ctx->nodes[node];
+  const bool hand = ns.cfg.kind == HOLD_KIND_HAND;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* pe = nullptr;
+  if (hand) {
+    HOLD_REQUIRE(pose_cond != nullptr, "hand node needs pose_cond [B,45] (zeros give lin_pose's bias, texture_net.py:80-82)");
+    WS(WS_PE, float, (size_t)B * 8, pe_ws);
+    pe = pe_ws;
+    k_pose_embed<<<ceil_div(B * 8, 64), 64, 0, s>>>(B, pose_cond, ns.lin_pose_w, ns.lin_pose_b, pe);
+    HOLD_LAUNCH_CHECK(ctx);
+  } else {
+    HOLD_REQUIRE(time_code != nullptr, "object node needs time_code [B,32]");
+  }
+  return launch_rgb(ctx, ns, P, P / B, x_c, normals, pe, feat, hand ? nullptr : time_code, rgb, s);
+}
+
+int hold_forward_warp(hold_ctx* ctx, int node, int B, int P, const float* x_c, const hold_node_pose* pose, float* x_d,
+                      int32_t* knn_idx, uint8_t* outlier_mask, void* stream) {
+  int rc = check_node(ctx, node, false);
+  if (rc) return rc;
+  HOLD_REQUIRE(B >= 0 && P >= 0, "negative size");
+  if (B * P == 0) return HOLD_OK;
+  HOLD_REQUIRE(x_c && pose && x_d && pose->tfs, "NULL argument");
+  NodeState& ns = ctx->nodes[node];
+  dim3 grid(ceil_div(P, 128), B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ns.cfg.kind == HOLD_KIND_HAND) {
+    if (!ns.has_rig) { set_error("hand node has no rig (hold_node_set_rig)"); return HOLD_E_STATE; }
+    k_inverse_warp<true, false, true><<<grid, 128, 0, s>>>(P, 1, 1, nullptr, nullptr, nullptr, x_c, pose->tfs, ns.cano_verts, ns.skin_w, x_d,
+                                                           knn_idx, outlier_mask, nullptr, ctx->dev_err);
+  } else {
+    k_inverse_warp<false, false, true><<<grid, 128, 0, s>>>(P, 1, 1, nullptr, nullptr, nullptr, x_c, pose->tfs, nullptr, nullptr, x_d,
+                                                            nullptr, nullptr, nullptr, ctx->dev_err);
+  }
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
 }
 
 int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose, float* x_c,

@@ -53,6 +53,7 @@ struct NodeState {
   float* lin_pose_b = nullptr;  // [8]
   float* cano_verts = nullptr;  // [778,3]
   float* skin_w = nullptr;      // [778,16]
+  unsigned short* knn_perm = nullptr;   // [49*16] vertex groups of the cluster-pruned KNN (knn_phases.h), 0xFFFF = padding
   SamplerState* sstate = nullptr;
 };
 
@@ -74,8 +75,7 @@ struct hold_ctx {
   bool has_bg = false;
   int bg_mlp_mode = 0;             // HOLD_MLP_* of the background nets (hold_bg_set_weights)
   hold::TcBg* bg_tc = nullptr;
-  int knn_variant = 0;             // A/B hook (hold_debug_set), 0 = production kernel
-  int tc_acc_comp = 0;             // experiment hook (hold_debug_set key 2): accumulator scale 1 + c * 2^-24 in the SDF chains
+  int tc_acc_comp = -1;            // measurement hook (hold_debug_set key 2): accumulator scale 1 + c * 2^-24 in the SDF chains; < 0: kTcAccComp
 };
 
 namespace hold {
@@ -112,7 +112,9 @@ __host__ __device__ inline float torch_linspace(float start, float end, int step
   if (steps == 1) return start;
   float step = (end - start) / (float)(steps - 1);
   int half = steps / 2;
-  return (i < half) ? (start + step * (float)i) : (end - step * (float)(steps - i - 1));
+  // ATen's linspace kernels (CPU and CUDA) evaluate start + step * i as one fused multiply-add (checked against torch.linspace
+  // bit for bit, tests/test_cpu_host.py); spelled out so that host and device builds agree
+  return (i < half) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(steps - i - 1), end);
 }
 
 // LaplaceDensity.density_func (engine/density.py:21-26)

@@ -59,61 +59,6 @@ __device__ __forceinline__ void knn15(const float* __restrict__ sv /*smem [778*3
   }
 }
 
-// Same result as knn15 for a point whose neighbour set is probably close to `r`'s current one (the previous sample
-// on the same ray).  Re-rank the 15 previous neighbours for the new point: their largest distance tau bounds the
-// 15th-nearest distance from above, so the scan over all 778 vertices only has to COLLECT the few vertices below tau
-// (a 2-instruction append to a per-thread list in shared memory) instead of running knn15's divergent sorted
-// insertion for most vertices; the collected candidates are merged afterwards.  Order is lexicographic
-// (distance, index), exactly what knn15 produces.
-constexpr int kKnnCand = 48;
-__device__ __forceinline__ void knn_insert(Knn15& r, float dist, int v) {
-  r.d[kKnn - 1] = dist;
-  r.i[kKnn - 1] = v;
-#pragma unroll
-  for (int k = kKnn - 1; k > 0; --k) {
-    bool sw = (r.d[k] < r.d[k - 1]) || (r.d[k] == r.d[k - 1] && r.i[k] < r.i[k - 1]);
-    if (sw) {
-      float td = r.d[k]; r.d[k] = r.d[k - 1]; r.d[k - 1] = td;
-      int ti = r.i[k]; r.i[k] = r.i[k - 1]; r.i[k - 1] = ti;
-    }
-  }
-}
-__device__ __forceinline__ float knn_dist(const float* __restrict__ sv, int v, float px, float py, float pz) {
-  float dx = px - sv[3 * v], dy = py - sv[3 * v + 1], dz = pz - sv[3 * v + 2];
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
-__device__ __forceinline__ void knn15_seeded(const float* __restrict__ sv, float px, float py, float pz, Knn15& r,
-                                             unsigned short* __restrict__ cand /* smem, [kKnnCand] of this thread */) {
-  int seed[kKnn];
-#pragma unroll
-  for (int k = 0; k < kKnn; ++k) { seed[k] = r.i[k]; r.d[k] = 3.0e38f; r.i[k] = 0x7fffffff; }
-#pragma unroll
-  for (int s = 0; s < kKnn; ++s) knn_insert(r, knn_dist(sv, seed[s], px, py, pz), seed[s]);
-  const float tau = r.d[kKnn - 1];
-  const int itau = r.i[kKnn - 1];
-  int cnt = 0;
-  for (int v = 0; v < kVerts; ++v) {
-    const float dist = knn_dist(sv, v, px, py, pz);
-    if (dist < tau || (dist == tau && v < itau)) {
-      if (cnt < kKnnCand) cand[cnt] = (unsigned short)v;
-      ++cnt;
-    }
-  }
-  if (cnt > kKnnCand) {  // seeds were poor (large step along the ray): full scan
-    knn15(sv, px, py, pz, r);
-    return;
-  }
-  for (int c = 0; c < cnt; ++c) {
-    const int v = cand[c];
-    bool present = false;
-#pragma unroll
-    for (int k = 0; k < kKnn; ++k) present |= (r.i[k] == v);
-    if (present) continue;
-    const float dist = knn_dist(sv, v, px, py, pz);
-    if (dist < r.d[kKnn - 1] || (dist == r.d[kKnn - 1] && v < r.i[kKnn - 1])) knn_insert(r, dist, v);
-  }
-}
-
 // query_skinning_weights_multi (model/mano/deformer.py:84-105) + blend of the 16 bone transforms
 // (`einsum("bpn,bnij->bpij")`, deformer.py:165): returns the top three rows of T = sum_j w_j tfs_j and
 // s = sum_j w_j tfs_j[3][3] (== sum of weights).
@@ -169,7 +114,9 @@ __device__ __forceinline__ bool inv3(const float* A /*row-major 3x3 with row str
 //   MODE_X: x given directly ([B, P, 3])
 // hand:   x_c = (T^-1 [x;1])[:3]  with T the KNN-weighted blend (skinning(inverse=True), deformer.py:162-166)
 // object: x_c = (tfs^-1 [x;1])[:3] (obj/deformer.py:21-31)
-template <bool HAND, bool FROM_Z>
+// FWD (forward_skinning, deformer.py:70-82 / obj/deformer.py:40-46): the input is a CANONICAL point, the KNN runs against the
+// canonical vertices (`verts`, one set for all frames: vert_stride 0) and the blend is applied as is: x_d = (T [x_c;1])[:3].
+template <bool HAND, bool FROM_Z, bool FWD = false>
 __global__ void __launch_bounds__(128)
 k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
                const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ xin,
@@ -182,12 +129,12 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
   __shared__ float sinv[12];
   const int b = blockIdx.y;
   if (HAND) {
-    for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
+    for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(FWD ? (size_t)0 : (size_t)b * kVerts * 3) + t];
     for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
   } else {
     if (threadIdx.x < 16) stf[threadIdx.x] = tfs[b * 16 + threadIdx.x];
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !FWD) {
       float Ai[9];
       bool ok = inv3(stf, 4, Ai);
       float s = stf[15];
@@ -221,17 +168,28 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
     knn15(sv, x, y, z, nn);
     float T[12], s, dmin;
     blend_tf(nn, skin_w, stf, T, s, dmin);
-    float Ai[9];
-    inv3(T, 4, Ai);
-    float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
-    ox = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
-    oy = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
-    oz = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
+    if (FWD) {
+      ox = (T[0] * x + T[1] * y + T[2] * z + T[3]) / s;
+      oy = (T[4] * x + T[5] * y + T[6] * z + T[7]) / s;
+      oz = (T[8] * x + T[9] * y + T[10] * z + T[11]) / s;
+    } else {
+      float Ai[9];
+      inv3(T, 4, Ai);
+      float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
+      ox = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
+      oy = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
+      oz = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
+    }
     if (knn_idx != nullptr) {
 #pragma unroll
       for (int k = 0; k < kKnn; ++k) knn_idx[gp * kKnn + k] = nn.i[k];
     }
     if (outlier != nullptr) outlier[gp] = dmin > 0.1f;
+  } else if (FWD) {
+    const float w = stf[12] * x + stf[13] * y + stf[14] * z + stf[15];
+    ox = (stf[0] * x + stf[1] * y + stf[2] * z + stf[3]) / w;
+    oy = (stf[4] * x + stf[5] * y + stf[6] * z + stf[7]) / w;
+    oz = (stf[8] * x + stf[9] * y + stf[10] * z + stf[11]) / w;
   } else {
     ox = sinv[0] * x + sinv[1] * y + sinv[2] * z + sinv[3];
     oy = sinv[4] * x + sinv[5] * y + sinv[6] * z + sinv[7];
@@ -240,133 +198,50 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
   xc[3 * gp] = ox, xc[3 * gp + 1] = oy, xc[3 * gp + 2] = oz;
 }
 
-// Hand-node variant of k_inverse_warp<true, true> that walks `kSeg` consecutive samples of one ray per thread and
-// seeds each sample's KNN from the previous one (knn15_seeded).  Same arithmetic, same results.
+// Hand-node variant of k_inverse_warp<true, true> for the hot path (sampler rounds, shading): a thread walks `kSeg` consecutive
+// samples of one ray and finds each sample's 15 nearest posed vertices with the seeded, cluster-pruned exact search of
+// knn_phases.h (same neighbours, same order as the full scan of knn15).  A warp holds 32 CONSECUTIVE rays at the same depth
+// segment, so its lanes prune nearly the same vertex groups.  Same arithmetic downstream, same results.
 constexpr int kSeg = 32;
 __global__ void __launch_bounds__(128)
 k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
                          const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
-                         const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
-                         const SamplerState* __restrict__ st) {
+                         const float* __restrict__ verts, const float* __restrict__ skin_w, const unsigned short* __restrict__ perm,
+                         float* __restrict__ xc, const SamplerState* __restrict__ st) {
   if (st != nullptr && st->done) return;
-  __shared__ float sv[kVerts * 3];
+  __shared__ float sv[kVerts * 3];                               // original order: seeds are original indices
+  __shared__ knnc::V4 svc[knnc::kNCl * knnc::kClSize];           // cluster order
+  __shared__ knnc::Cl scl[knnc::kNCl];
   __shared__ float stf[kJoints * 16];
-  __shared__ unsigned short scand[128 * kKnnCand];
-  unsigned short* cand = scand + threadIdx.x * kKnnCand;
+  __shared__ unsigned short scand[128 * knnc::kCand];
+  unsigned short* cand = scand + threadIdx.x * knnc::kCand;
   const int b = blockIdx.y;
   for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
   for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
+  for (int j = threadIdx.x; j < knnc::kNCl * knnc::kClSize; j += blockDim.x) {
+    const int v = perm[j];
+    knnc::V4 e;
+    if (v == 0xFFFF) { e.x = e.y = e.z = 1.0e18f; e.idx = -1; }
+    else { const float* pv = verts + ((size_t)b * kVerts + v) * 3; e.x = pv[0], e.y = pv[1], e.z = pv[2]; e.idx = v; }
+    svc[j] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x < knnc::kNCl) scl[threadIdx.x] = knnc::make_cluster(svc + threadIdx.x * knnc::kClSize);
   __syncthreads();
   const int segs = (ns + kSeg - 1) / kSeg;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rays_per_frame * segs) return;
-  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
+  const int seg = t / rays_per_frame, ray_in_frame = t - seg * rays_per_frame;
   const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
   const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
   const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
-  Knn15 nn;
+  knnc::Top top;
   const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
   for (int k = k0; k < k1; ++k) {
     const float tz = zbuf[ray * zstride + k];
     const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
-    if (k == k0) knn15(sv, x, y, z, nn);
-    else knn15_seeded(sv, x, y, z, nn, cand);
-    float T[12], s, dmin;
-    blend_tf(nn, skin_w, stf, T, s, dmin);
-    float Ai[9];
-    inv3(T, 4, Ai);
-    const float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
-    const size_t gp = ray * ns + k;
-    xc[3 * gp] = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
-    xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
-    xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
-  }
-}
-
-// HOLD_KNN_OCC=1 (round-2 A/B): the same kernel text compiled for >= 6 resident blocks per SM (<= 85 registers)
-__global__ void __launch_bounds__(128, 6)
-k_inverse_warp_hand_rays_occ(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
-                         const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
-                         const float* __restrict__ verts, const float* __restrict__ skin_w, float* __restrict__ xc,
-                         const SamplerState* __restrict__ st) {
-  if (st != nullptr && st->done) return;
-  __shared__ float sv[kVerts * 3];
-  __shared__ float stf[kJoints * 16];
-  __shared__ unsigned short scand[128 * kKnnCand];
-  unsigned short* cand = scand + threadIdx.x * kKnnCand;
-  const int b = blockIdx.y;
-  for (int t = threadIdx.x; t < kVerts * 3; t += blockDim.x) sv[t] = verts[(size_t)b * kVerts * 3 + t];
-  for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
-  __syncthreads();
-  const int segs = (ns + kSeg - 1) / kSeg;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rays_per_frame * segs) return;
-  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
-  const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
-  const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
-  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
-  Knn15 nn;
-  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
-  for (int k = k0; k < k1; ++k) {
-    const float tz = zbuf[ray * zstride + k];
-    const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
-    if (k == k0) knn15(sv, x, y, z, nn);
-    else knn15_seeded(sv, x, y, z, nn, cand);
-    float T[12], s, dmin;
-    blend_tf(nn, skin_w, stf, T, s, dmin);
-    float Ai[9];
-    inv3(T, 4, Ai);
-    const float rx = x - T[3] / s, ry = y - T[7] / s, rz = z - T[11] / s;
-    const size_t gp = ray * ns + k;
-    xc[3 * gp] = Ai[0] * rx + Ai[1] * ry + Ai[2] * rz;
-    xc[3 * gp + 1] = Ai[3] * rx + Ai[4] * ry + Ai[5] * rz;
-    xc[3 * gp + 2] = Ai[6] * rx + Ai[7] * ry + Ai[8] * rz;
-  }
-}
-
-// HOLD_KNN_FILTER=1 (round-2 A/B): the same walk with the filtered exact KNN of knn_phases.h (one 16-byte shared load + 3 FMA per
-// vertex in the scan instead of 3 loads + 9 instructions; bit-identical neighbours, tests/test_cpu_knn_filter.py).
-__global__ void __launch_bounds__(128)
-k_inverse_warp_hand_rays_filt(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf, const float* __restrict__ cam,
-                              const float* __restrict__ dirs, const float* __restrict__ tfs, const float* __restrict__ verts,
-                              const float* __restrict__ skin_w, float* __restrict__ xc, const SamplerState* __restrict__ st) {
-  if (st != nullptr && st->done) return;
-  __shared__ knnf::V4 sv4[kVerts];
-  __shared__ float stf[kJoints * 16];
-  __shared__ unsigned short scand[128 * knnf::kCand];
-  __shared__ float s_qmax;
-  unsigned short* cand = scand + threadIdx.x * knnf::kCand;
-  const int b = blockIdx.y;
-  for (int v = threadIdx.x; v < kVerts; v += blockDim.x) {
-    const float* pv = verts + ((size_t)b * kVerts + v) * 3;
-    knnf::V4 e;
-    e.x = pv[0], e.y = pv[1], e.z = pv[2];
-    e.q = e.x * e.x + e.y * e.y + e.z * e.z;
-    sv4[v] = e;
-  }
-  for (int t = threadIdx.x; t < kJoints * 16; t += blockDim.x) stf[t] = tfs[(size_t)b * kJoints * 16 + t];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float q = 0.f;
-    for (int v = 0; v < kVerts; ++v) q = fmaxf(q, sv4[v].q);
-    s_qmax = q;
-  }
-  __syncthreads();
-  const float qmax = s_qmax;
-  const int segs = (ns + kSeg - 1) / kSeg;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rays_per_frame * segs) return;
-  const int ray_in_frame = t / segs, seg = t - ray_in_frame * segs;
-  const size_t ray = (size_t)b * rays_per_frame + ray_in_frame;
-  const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
-  const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
-  knnf::Top top;
-  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
-  for (int k = k0; k < k1; ++k) {
-    const float tz = zbuf[ray * zstride + k];
-    const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));
-    if (k == k0) knnf::full_scan(sv4, x, y, z, top);
-    else knnf::seeded_filter(sv4, qmax, x, y, z, top, cand);
+    if (k == k0) knnc::full_scan(svc, x, y, z, top);
+    else knnc::seeded_clustered(sv, svc, scl, x, y, z, top, cand);
     Knn15 nn;
 #pragma unroll
     for (int j = 0; j < kKnn; ++j) { nn.d[j] = top.d[j]; nn.i[j] = top.i[j]; }

@@ -35,6 +35,13 @@ constexpr int kTcThreads = 192;
 // half of every |x| < 0.125 is subnormal; measured: the split then gains only 2x over bf16).  The accumulator is
 // rescaled by 2^-16 in the epilogue's bias FMA.  Range: |a| < 1023, |w| < 64.
 constexpr float kTcScaleA = 64.0f, kTcScaleW = 1024.0f, kTcUnscale = 1.0f / (64.0f * 1024.0f);
+// Accumulator-truncation compensation of the Softplus chains.  tcgen05.mma adds into its fp32 accumulator with truncation (round
+// toward zero), not round-to-nearest: measured against float64 on hardware (profiles/r02_tc_accumulator_bias.md) every layer of
+// 48 accumulations (K = 256 x 3 passes) comes out SHRUNK by ~12 x 2^-24 relative — a bias, identical for the hand and object
+// nets and for perturbed weights (zero crossing of the mean sdf error at c = 11.1 / 11.0 / 12.4 / 12.9).  Undoing it in the
+// epilogue's unscale multiply (free) cuts the sdf error 5-8x (5.99e-6 -> 9.5e-7 of the sdf scale), which is what the Laplace
+// density needs at small beta (error amplification 1 / (2 beta^2), engine/density.py:21-26).
+constexpr int kTcAccComp = 12;
 
 constexpr int kTcMaxSteps = 17;
 struct TcLayer {
@@ -897,7 +904,7 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
-  a.unscale = kTcUnscale * (1.0f + (float)ctx->tc_acc_comp * (1.0f / 16777216.0f));
+  a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));
   const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
   if (rev) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");

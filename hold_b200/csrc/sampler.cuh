@@ -25,7 +25,7 @@ struct SamplerArgs {
   // training-mode randomness (NULL in eval)
   const float* jitter;
   const float* u_rand;
-  const int* extra_idx;
+  const int* extra_idx;  // [max_iters, n_extra]: row (rounds - 1) is used
   float* z_out;  // [R, n_samples + n_extra + 2]
   int* iters_out;
 };
@@ -52,6 +52,25 @@ __device__ __forceinline__ float warp_excl_scan(float v, int lane) {
   float e = __shfl_up_sync(0xffffffffu, x, 1);
   return lane == 0 ? 0.f : e;
 }
+
+// The reference's cumsums run on torch tensors whose CPU kernel accumulates in double and rounds every output to float
+// (at::acc_type<float, false>); a CUDA scan accumulates in float.  Either way each prefix is within an ulp of the exact sum.
+// The kernels here keep the TERMS in float (as the reference does) and accumulate the prefixes in double: the inverse-CDF step
+// thresholds cdf[i+1] - cdf[i] at 1e-5 (ray_sampler.py:304), and in empty space that difference is 1e-5 / (1 + 639e-5) =
+// 0.994e-5 — one float ulp of a two-level float scan is enough to flip the branch (measured: 1.8 % of the final samples moved
+// by up to a bin width with float prefixes, tests/test_gpu_sampler_rounds.py).
+__device__ __forceinline__ double warp_excl_scan_d(double v, int lane) {
+  double x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  double e = __shfl_up_sync(0xffffffffu, x, 1);
+  return lane == 0 ? 0.0 : e;
+}
+
+__device__ __forceinline__ float expf_cr(float x) { return (float)exp((double)x); }
 
 // in-place bitonic sort (ascending) of n = power of two floats in shared memory by one warp, with payload
 __device__ __forceinline__ void warp_bitonic(float* key, float* val, int n, int lane) {
@@ -184,24 +203,23 @@ __device__ __forceinline__ float error_bound(const RaySmem& m, int n, float beta
   const int nb = n - 1;
   const int seg = (nb + 31) / 32;
   const int lo = min(lane * seg, nb), hi = min(lo + seg, nb);
-  float accI = 0.f, accE = 0.f;
+  double accI = 0.0, accE = 0.0;
   const float inv4b2 = 4.0f * beta * beta;
   for (int i = lo; i < hi; ++i) {
-    float d = m.delta[i];
-    float sig = laplace_density(m.s[i], beta);
-    accI += d * sig;                                 // free energy of interval i (contributes to I_{i+1})
-    accE += expf(-m.dstar[i] / beta) * (d * d) / inv4b2;
-    m.t0[i] = accI;                                  // lane-local inclusive sums
-    m.t1[i] = accE;
+    const float d = m.delta[i];
+    const float fe = d * laplace_density(m.s[i], beta);              // free energy of interval i (contributes to I_{i+1})
+    const float es = expf(-m.dstar[i] / beta) * (d * d) / inv4b2;
+    m.t0[i] = fe, m.t1[i] = es;                                      // float terms, double prefixes
+    accI += (double)fe, accE += (double)es;
   }
-  float offI = warp_excl_scan(accI, lane), offE = warp_excl_scan(accE, lane);
+  double runI = warp_excl_scan_d(accI, lane), runE = warp_excl_scan_d(accE, lane);
   float best = -INFINITY;
-  float prevI = 0.f;
   for (int i = lo; i < hi; ++i) {
-    float Iex = offI + prevI;  // exclusive: sum_{j<i} delta_j sigma_j
-    float Ein = offE + m.t1[i];
-    prevI = m.t0[i];
-    float bo = (fminf(expf(Ein), 1.0e6f) - 1.0f) * expf(-Iex);
+    const float Iex = (float)runI;   // exclusive: sum_{j<i} delta_j sigma_j
+    runI += (double)m.t0[i];
+    runE += (double)m.t1[i];
+    const float Ein = (float)runE;
+    const float bo = (fminf(expf(Ein), 1.0e6f) - 1.0f) * expf(-Iex);
     best = fmaxf(best, bo);
   }
   return warp_max(best);
@@ -295,48 +313,62 @@ __global__ void __launch_bounds__(128) k_sampler_resample(SamplerArgs a, int it)
   compute_dstar(m, n, lane);
   const float beta = a.beta[r];
   // lane-segment scans over the n samples: free energy (exclusive -> transmittance) and, when upsampling,
-  // the error integral (inclusive) over the n-1 intervals
+  // the error integral (inclusive) over the n-1 intervals.  Float terms, double prefixes (see warp_excl_scan_d).
   const int seg = (n + 31) / 32;
   const int lo = min(lane * seg, n), hi = min(lo + seg, n);
-  float accF = 0.f, accE = 0.f;
+  double accF = 0.0, accE = 0.0;
   const float inv4b2 = 4.0f * beta * beta;
   for (int i = lo; i < hi; ++i) {
-    float d = (i < n - 1) ? m.delta[i] : 1.0e10f;
-    float fe = d * laplace_density(m.s[i], beta);
-    m.t0[i] = accF;  // lane-local exclusive
-    accF += fe;
+    const float d = (i < n - 1) ? m.delta[i] : 1.0e10f;
+    const float fe = d * laplace_density(m.s[i], beta);
+    accF += (double)fe;
     if (i < n - 1) {
-      accE += expf(-m.dstar[i] / beta) * (d * d) / inv4b2;
-      m.t1[i] = accE;  // lane-local inclusive
+      const float es = expf(-m.dstar[i] / beta) * (d * d) / inv4b2;
+      accE += (double)es;
+      m.t1[i] = es;
     }
     m.delta[i] = fe;   // reuse: free energy
   }
-  float offF = warp_excl_scan(accF, lane), offE = warp_excl_scan(accE, lane);
-  float psum = 0.f;
+  double runF = warp_excl_scan_d(accF, lane), runE = warp_excl_scan_d(accE, lane);
+  double psum = 0.0;
   for (int i = lo; i < hi; ++i) {
     if (i < n - 1) {
-      float T = expf(-(offF + m.t0[i]));
+      const float T = expf(-(float)runF);      // exclusive prefix of the free energy
+      runE += (double)m.t1[i];
       float pdf;
-      if (upsample) pdf = (fminf(expf(offE + m.t1[i]), 1.0e6f) - 1.0f) * T + a.add_tiny;
-      else pdf = (1.0f - expf(-m.delta[i])) * T + 1e-5f;
+      // exp(E) - 1 and 1 - exp(-fe) cancel to a few ulps of 1 where E resp. fe are tiny (empty space), and those ulps ARE the pdf
+      // there (floor 1e-6 / 1e-5): the inverse CDF integrates them over hundreds of bins.  expf_cr is the correctly rounded float
+      // exponential (what a <= 1 ulp libm such as the reference's returns almost always); CUDA's expf (2 ulp) measurably moved
+      // 1.8 % of the final samples beyond 1e-4 R_s of the exact answer against the reference's own 0.2 % (teacher-forced test).
+      if (upsample) pdf = (fminf(expf_cr((float)runE), 1.0e6f) - 1.0f) * T + a.add_tiny;
+      else pdf = (1.0f - expf_cr(-m.delta[i])) * T + 1e-5f;
       m.dstar[i] = pdf;
-      psum += pdf;
+      psum += (double)pdf;
     }
+    runF += (double)m.delta[i];
   }
-  float total = warp_sum(psum);
+  // pdf.sum(-1): float result of a double accumulation
+  double tot_d = psum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot_d += __shfl_xor_sync(0xffffffffu, tot_d, o);
+  const float total = (float)tot_d;
   // cdf[0] = 0, cdf[i+1] = cumsum(pdf/total) -> stored in t0[0..n)
-  float accC = 0.f;
+  double accC = 0.0;
   const int nb = n - 1;
   const int segb = (nb + 31) / 32;
   const int lob = min(lane * segb, nb), hib = min(lob + segb, nb);
   __syncwarp();
   for (int i = lob; i < hib; ++i) {
-    accC += m.dstar[i] / total;
-    m.t1[i] = accC;
+    const float pn = m.dstar[i] / total;
+    m.t1[i] = pn;
+    accC += (double)pn;
   }
-  float offC = warp_excl_scan(accC, lane);
+  double runC = warp_excl_scan_d(accC, lane);
   __syncwarp();
-  for (int i = lob; i < hib; ++i) m.t0[i + 1] = offC + m.t1[i];
+  for (int i = lob; i < hib; ++i) {
+    runC += (double)m.t1[i];
+    m.t0[i + 1] = (float)runC;
+  }
   if (lane == 0) m.t0[0] = 0.f;
   __syncwarp();
   const float* cdf = m.t0;
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(128) k_sampler_resample(SamplerArgs a, int it)
   const int Nx = a.n_extra, S = N + Nx + 2;
   if (lane == 0) { out[N] = a.near; out[N + 1] = a.far[r]; }
   for (int k = lane; k < Nx; k += 32) {
-    int idx = (a.extra_idx != nullptr) ? a.extra_idx[k] : (int)torch_linspace(0.f, (float)(n - 1), Nx, k);
+    int idx = (a.extra_idx != nullptr) ? min(max(a.extra_idx[it * Nx + k], 0), n - 1) : (int)torch_linspace(0.f, (float)(n - 1), Nx, k);
     out[N + 2 + k] = m.z[idx];
   }
   int sp2 = 1;

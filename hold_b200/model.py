@@ -52,7 +52,10 @@ class ImplicitNet(nn.Module):
             setattr(self, f"lin{l}", _wn_linear(dims[l] if l > 0 else d0, out))
         object.__setattr__(self, "_node", None)
 
-    def forward(self, x, cond=None):
+    def forward(self, input, cond, current_epoch=None):
+        """Same signature as networks/shape_net.py:84.  `cond` is accepted and unused: the hand's pose condition is multiplied
+        by zero in the reference (shape_net.py:104-106) and the object has none."""
+        x = input
         if x.ndim == 2:
             x = x.unsqueeze(0)
         Bn, P, _ = x.shape
@@ -207,9 +210,21 @@ class ObjectServer(nn.Module):
         self.ctx = ctx
         dev = torch.device("cuda", ctx.device)
         self.v3d_cano = pts_cano.to(dev).float().contiguous()
-        self.obj_scale = float(obj_scale)
-        nm = torch.eye(4) if norm_mat is None else norm_mat
-        self.denorm_mat = torch.linalg.inv(nm.float()).to(dev).contiguous()
+        self.set_object_model(obj_scale=obj_scale, norm_mat=norm_mat)
+
+    def set_object_model(self, obj_scale=None, norm_mat=None, v3d_cano=None):
+        """The registered buffers of the reference's ObjectModel (model/obj/object_model.py:23-27): `obj_scale`, `norm_mat`
+        (-> `denorm_mat` = its inverse), `v3d_cano`.  Real sequences carry non-trivial values (data.npy); a reference checkpoint
+        stores them under `nodes.object.server.object_model.*` (checkpoint.load_reference_state_dict feeds them here)."""
+        dev = torch.device("cuda", self.ctx.device)
+        if v3d_cano is not None:
+            self.v3d_cano = v3d_cano.to(dev).float().contiguous()
+        if obj_scale is not None:
+            self.obj_scale = obj_scale if (torch.is_tensor(obj_scale) and obj_scale.requires_grad) else float(torch.as_tensor(obj_scale).reshape(-1)[0])
+        if norm_mat is not None or not hasattr(self, "norm_mat"):
+            nm = torch.eye(4) if norm_mat is None else norm_mat.detach().float().cpu().reshape(4, 4)
+            self.norm_mat = nm.to(dev).contiguous()
+            self.denorm_mat = torch.linalg.inv(nm.double()).float().to(dev).contiguous()
         self.verts_c = self.v3d_cano[None]
 
     def forward(self, scene_scale, transl, thetas, absolute=False):
@@ -246,7 +261,7 @@ class Node(nn.Module):
     density.beta, frame_latent_encoder.weight (object)."""
 
     def __init__(self, ctx, slot, node_id, sampler_cfg, bounding_sphere, n_frames=1, mano=None, betas=None, obj_pts=None,
-                 mlp_mode=capi.MLP_FP32, beta=0.1):
+                 mlp_mode=capi.MLP_FP32, beta=0.1, obj_scale=1.0, norm_mat=None):
         super().__init__()
         self.ctx, self.slot, self.node_id = ctx, slot, node_id
         self.kind = "hand" if node_id in ("right", "left") else "object"
@@ -261,7 +276,7 @@ class Node(nn.Module):
         if self.kind == "hand":
             self.server = MANOServer(ctx, mano, betas)
         else:
-            self.server = ObjectServer(ctx, obj_pts)
+            self.server = ObjectServer(ctx, obj_pts, obj_scale=obj_scale, norm_mat=norm_mat)   # data.npy: entities.object.{obj_scale,norm_mat}
             self.frame_latent_encoder = nn.Embedding(n_frames, 32)
         # per-frame pose parameters, same module names as the reference (model/generic/params.py) so that a reference
         # checkpoint loads (hold_b200/checkpoint.py); used when the input dict carries only frame ids
@@ -345,7 +360,12 @@ class ErrorBoundSampler:
         rnd = None
         if rand is not None:
             rnd = capi.SamplerRand()
-            rnd.jitter, rnd.u, rnd.extra_idx = rand["jitter"].data_ptr(), rand["u"].data_ptr(), rand["extra_idx"].data_ptr()
+            ex = rand["extra_idx"].to(torch.int32)
+            if ex.dim() == 1:   # one draw for every round count (valid when it indexes below N_samples_eval)
+                ex = ex[None].repeat(n.sampler_cfg["max_total_iters"], 1)
+            ex = ex.contiguous()
+            self._keep = ex
+            rnd.jitter, rnd.u, rnd.extra_idx = rand["jitter"].data_ptr(), rand["u"].data_ptr(), ex.data_ptr()
         check(lib().hold_sample(n.ctx.h, n.slot, R, B, ptr(cam_loc), ptr(ray_dirs), C.byref(pose),
                                 C.byref(rnd) if rnd is not None else None, ptr(z), ptr(iters), stream_ptr()))
         return z, iters
@@ -409,10 +429,10 @@ class HOLDNet(nn.Module):
             self.background.sync_weights()
 
     @torch.no_grad()
-    def forward(self, input):
+    def forward(self, input, chunk=None):
         """HOLDNet.forward + composite (hold/hold_net.py:110-134), eval: rgb = fg_rgb + bg_rgb, semantics,
-        bg_rgb_only, instance_map = argmax(semantics)."""
-        out = self.forward_fg(input, return_factors=False)
+        bg_rgb_only, instance_map = argmax(semantics).  chunk: see forward_fg."""
+        out = self.forward_fg(input, return_factors=False, chunk=chunk)
         B = input["uv"].shape[0]
         bg = self.background(out["bg_weights"], out["ray_dirs"], out["cam_loc"], input["idx"], B)
         out["bg_z_vals"] = bg["bg_z_vals"]
@@ -423,7 +443,30 @@ class HOLDNet(nn.Module):
         return out
 
     @torch.no_grad()
-    def forward_fg(self, input, return_factors=True, want_weights=True):
+    def forward_fg(self, input, return_factors=True, want_weights=True, chunk=None):
+        """chunk: rays per call.  The sampler's convergence flag `beta.max() > beta0` is global over the rays of ONE call
+        (engine/ray_sampler.py:244); the reference's render path issues 512-pixel calls (datasets/eval_datasets.py:13,
+        hold.py:190-192), so `chunk=512` reproduces its per-chunk round counts, while `chunk=None` renders the whole frame in
+        one call (all rays run as many rounds as the slowest ray of the frame needs)."""
+        if chunk is not None and input["uv"].shape[1] > chunk:
+            assert input["uv"].shape[0] == 1, "chunked rendering follows the reference's eval path: one frame per call"
+            outs = []
+            for s0 in range(0, input["uv"].shape[1], chunk):
+                sub = dict(input)
+                sub["uv"] = input["uv"][:, s0:s0 + chunk].contiguous()
+                outs.append(self.forward_fg(sub, return_factors=return_factors, want_weights=want_weights, chunk=None))
+            out = {}
+            for k, v in outs[0].items():
+                if k == "sampler_iters":
+                    out[k] = torch.stack([o[k] for o in outs]).amax(0)
+                    out["sampler_iters_per_chunk"] = torch.stack([o[k] for o in outs])
+                elif k == "factors":
+                    out[k] = {nid: {kk: torch.cat([o[k][nid][kk] for o in outs]) for kk in v[nid]} for nid in v}
+                elif torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == outs[0]["ray_dirs"].shape[0]:
+                    out[k] = torch.cat([o[k] for o in outs])
+                else:
+                    out[k] = v
+            return out
         uv, ext, intr = input["uv"].float().contiguous(), input["extrinsics"].float().contiguous(), input["intrinsics"].float().contiguous()
         B, P, _ = uv.shape
         dev = uv.device

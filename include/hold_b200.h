@@ -116,11 +116,14 @@ typedef struct hold_render_out {
 } hold_render_out;
 
 /* Training-mode randomness is an INPUT (generated by torch on the host side of the boundary):
- * stratified jitter (ray_sampler.py:70-78), u (:292), extras permutation (:328).  All NULL in eval. */
+ * stratified jitter (ray_sampler.py:70-78), u (:292), extras permutation (:328).  All NULL in eval.
+ * The reference draws the extras as randperm(n)[:N_extra] with n = the size of the z buffer when the loop ends, i.e.
+ * rounds * N_eval — known only on the device.  The caller therefore supplies one draw per possible round count:
+ * extra_idx[j] = randperm((j + 1) * N_eval)[:N_extra]; the kernels use row (rounds - 1). */
 typedef struct hold_sampler_rand {
   const float* jitter;      /* [R, n_samples_eval] uniforms */
   const float* u;           /* [R, n_samples] uniforms */
-  const int32_t* extra_idx; /* [n_samples_extra] indices into the final z buffer */
+  const int32_t* extra_idx; /* [max_total_iters, n_samples_extra] indices into the final z buffer, one row per round count */
 } hold_sampler_rand;
 
 int hold_version(void);
@@ -243,9 +246,21 @@ int hold_background(hold_ctx* ctx, int R, int B, const float* cam_loc, const flo
  * (hold_utils.query_oc, meshing): ImplicitNet.forward on canonical points (shape_net.py:84-130). */
 int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c /*[P,3]*/, const float* embed_w,
                   float* sdf /*[P]*/, float* grad /*[P,3] or NULL*/, float* feat /*[P,256] or NULL*/, void* stream);
+
+/* RenderingNet.forward, mode "pose" (networks/texture_net.py:46-101): P = B x points-per-frame canonical points x_c [P,3],
+ * normals [P,3], feature vectors [P,256]; hand: pose_cond [B,45] (= cond["pose"], lin_pose applied inside); object:
+ * time_code [B,32] (the reference concatenates it to the features, engine/volsdf_utils.py:133-141).  -> rgb [P,3]. */
+int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const float* normals, const float* pose_cond,
+                  const float* feat, const float* time_code, float* rgb, void* stream);
 /* KNNDeformer.forward(inverse=True) / ObjectDeformer.forward(inverse=True): x [B,P,3] -> x_c, knn idx [B,P,15] (opt). */
 int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose,
                       float* x_c, int32_t* knn_idx, uint8_t* outlier_mask, void* stream);
+
+/* KNNDeformer.forward_skinning (model/mano/deformer.py:70-82) / ObjectDeformer.forward_skinning (model/obj/deformer.py:40-46):
+ * canonical points x_c [B,P,3] -> deformed points x_d [B,P,3]; hand: 15 nearest CANONICAL vertices, blended transform applied
+ * as is (skinning(inverse=False), deformer.py:167-170); knn_idx [B,P,15] / outlier_mask [B,P] optional (hand only). */
+int hold_forward_warp(hold_ctx* ctx, int node, int B, int P, const float* x_c, const hold_node_pose* pose, float* x_d,
+                      int32_t* knn_idx, uint8_t* outlier_mask, void* stream);
 
 /* Reverse mode of hold_inverse_warp w.r.t. the transforms (skinning weights are detached in the reference, deformer.py:101):
  * g_xc [B,P,3] -> g_tfs (hand [B,16,4,4], object [B,4,4]; the constant last row gets 0 except [3][3]) and, optionally, g_x

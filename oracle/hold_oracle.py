@@ -173,6 +173,8 @@ def final_z_vals(samples, z, far, cfg, rand=None):
             eidx = torch.linspace(0, z.shape[1] - 1, Nx).long()
         else:
             eidx = rand["extra_idx"]
+            if eidx.dim() == 2:   # one draw per possible round count (include/hold_b200.h, hold_sampler_rand): row rounds-1
+                eidx = eidx[z.shape[1] // cfg["N_samples_eval"] - 1]
         extra = torch.cat([near, far, z[:, eidx]], -1)
     else:
         extra = torch.cat([near, far], -1)

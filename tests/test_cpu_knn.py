@@ -1,6 +1,7 @@
-"""CPU-only: the filtered exact KNN-15 (hold_b200/csrc/knn_phases.h, HOLD_KNN_FILTER=1 variant of the hand inverse-warp
-kernel) is bit-identical to brute force in (distance, index) order — near the hand, far from it, on vertices, with duplicate
-vertices (ties) and across large steps along the ray (fallback path)."""
+"""CPU-only: the cluster-pruned, seeded exact KNN-15 of the hand inverse-warp kernel (hold_b200/csrc/knn_phases.h, run here on
+the host) is bit-identical to brute force in (distance, index) order — near the hand, far from it, on vertices, with duplicate
+vertices (ties), on an articulated (posed) hand whose groups were formed on the canonical one, and across large steps along
+the ray (fallback path)."""
 import ctypes as C
 import os
 import subprocess
@@ -20,18 +21,26 @@ def _lib():
     return C.CDLL(out)
 
 
-def test_filtered_knn_is_exact():
+def test_clustered_knn_is_exact():
     from hold_b200 import synth
 
     lib = _lib()
+    import torch
+    from oracle import hold_oracle as O
+
     m = synth.make_mano_struct(0)
-    verts = (m["v_template"].numpy() * 1.0 + np.array([0.3, -0.2, 0.1], np.float32)).astype(np.float32)
+    cano = np.ascontiguousarray(m["v_template"].numpy().astype(np.float32))
+    skin = np.ascontiguousarray(m["lbs_weights"].numpy().astype(np.float32))
+    g = torch.Generator().manual_seed(1)
+    pose = torch.randn(1, 48, generator=g) * 0.5                       # a strongly articulated hand: groups spread out
+    posed = O.mano_server(m, torch.ones(1) * 4.7, torch.tensor([[0.3, -0.2, 0.1]]), pose, torch.zeros(1, 10))["verts"][0]
+    verts = np.ascontiguousarray(posed.numpy().astype(np.float32))
     verts[100] = verts[7]                       # duplicate vertices: exact distance ties, resolved by index
     verts[650] = verts[7]
     rng = np.random.default_rng(0)
     n_rays, ns = 48, 96
     cam = (rng.normal(size=(n_rays, 3)) * 2.0 + np.array([0, 0, -4.0])).astype(np.float32)
-    target = verts[rng.integers(0, 778, n_rays)] + rng.normal(size=(n_rays, 3)).astype(np.float32) * 0.05
+    target = verts[rng.integers(0, 778, n_rays)] + rng.normal(size=(n_rays, 3)).astype(np.float32) * 0.05 * np.ptp(verts)
     dirs = target - cam
     dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
     z = np.sort(rng.uniform(0.0, 9.0, size=(n_rays, ns)).astype(np.float32), axis=1)
@@ -40,9 +49,12 @@ def test_filtered_knn_is_exact():
     cam[1] = verts[7]; z[1, 0] = 0.0             # a sample exactly on a (triplicated) vertex
     idx = np.zeros((n_rays, ns, 15), np.int32)
     dist = np.zeros((n_rays, ns, 15), np.float32)
-    fb = C.c_int(0)
+    fb, vis = C.c_int(0), C.c_double(0.0)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    assert lib.knn_filter_host(C.c_int(n_rays), C.c_int(ns), vp(verts), vp(cam), vp(dirs), vp(z), vp(idx), vp(dist), C.byref(fb)) == 0
+    assert lib.knn_cluster_host(C.c_int(n_rays), C.c_int(ns), vp(verts), vp(cano), vp(skin), vp(cam), vp(dirs), vp(z), vp(idx), vp(dist),
+                                C.byref(fb), C.byref(vis)) == 0
+    print(f"groups visited per sample: {vis.value:.1f} of 49; full-scan fallbacks: {fb.value} of {n_rays * (ns - 1)}")
+    assert vis.value < 25.0, "the pruning must prune"
     # brute force with the reference's float32 expression, points formed as cam + z * dir in float32 (two ops)
     pts = (cam[:, None, :] + (z[:, :, None] * dirs[:, None, :]).astype(np.float32)).astype(np.float32)
     diff = (pts[:, :, None, :] - verts[None, None, :, :]).astype(np.float32)

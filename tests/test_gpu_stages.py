@@ -76,6 +76,38 @@ def test_object_server(setup, ctx):
     close(out["verts"], s["art"]["object"]["verts"], 1e-5, "obj_verts")
 
 
+def test_object_server_with_object_model_buffers(setup, ctx):
+    """obj_scale != 1 and a non-identity norm_mat (real sequences: data.npy entities.object, model/obj/object_model.py:23-27),
+    set the way checkpoint.load_reference_state_dict sets them (from `nodes.object.server.object_model.*`)."""
+    from hold_b200 import checkpoint
+
+    s, O = setup, setup["O"]
+    sc = s["sc"]
+    node = s["net"].nodes["object"]
+    g = torch.Generator().manual_seed(12)
+    nm = torch.eye(4)
+    nm[:3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=g))[0] * 1.7
+    nm[:3, 3] = torch.tensor([0.11, -0.07, 0.23])
+    sd = {"model.nodes.object.server.object_model.obj_scale": torch.tensor([0.83]),
+          "model.nodes.object.server.object_model.norm_mat": nm,
+          "model.nodes.object.server.object_model.denorm_mat": torch.linalg.inv(nm),
+          "model.nodes.object.server.object_model.v3d_cano": node.server.v3d_cano.cpu().clone()}
+    bufs = checkpoint.object_model_buffers(sd)["object"]
+    old = (node.server.obj_scale, node.server.norm_mat.clone())
+    node.server.set_object_model(**bufs)
+    try:
+        _, _, out, tfs = node.articulate(s["inp"])
+        ctx.check()
+    finally:
+        node.server.set_object_model(obj_scale=old[0], norm_mat=old[1])
+    p = sc.params["object"]
+    scale = torch.full((sc.B,), float(sc.scene_scale))
+    tf, v = O.object_server(p["global_orient"], p["transl"], scale, 0.83, torch.linalg.inv(nm), sc.obj_pts_cano)
+    close(tfs, tf, 1e-5, "obj_tfs (obj_scale 0.83, norm_mat)")
+    close(out["verts"], v, 1e-5, "obj_verts (obj_scale 0.83, norm_mat)")
+    assert (tf - s["art"]["object"]["tfs"]).abs().max().item() > 1e-2, "the buffers must change the transform"
+
+
 def test_camera_rays(setup, ctx):
     from hold_b200 import ops
 
@@ -130,13 +162,20 @@ def test_sdf_eval(setup, ctx):
 def test_sdf_eval_barf_weights(setup, ctx):
     """BarfEmbedder.embed (engine/embedders.py:92-122): the object's Fourier embedding times the coarse-to-fine mask
     barf_weights(alpha) — mid-training (alpha = 2.6: frequencies 0,1 fully on, 2 partially, 3.. off), sdf, feature and the
-    gradient (which chains through the weighted embedding) against the oracle."""
+    gradient (which chains through the weighted embedding) against the oracle.  The geometric initialisation zeroes lin0's
+    weights on the Fourier columns (shape_net.py:57-60), so the test trains them away from zero first (+ N(0, 0.05^2))."""
     s, O = setup, setup["O"]
     g = torch.Generator().manual_seed(8)
     x = (torch.rand(1, 1500, 3, generator=g) - 0.5) * 1.6
     node = s["net"].nodes["object"]
     w = O.barf_weights(2.6)
     assert w.shape == (39,) and 0.0 < w[3 + 6 * 2].item() < 1.0 and w[-1].item() == 0.0, "the mask must be non-trivial"
+    sd0 = {k: v.clone() for k, v in s["sc"].sdf_state["object"].items()}
+    sd = {k: v.clone() for k, v in sd0.items()}
+    sd["lin0.weight_v"][:, 3:] += 0.05 * torch.randn(sd["lin0.weight_v"][:, 3:].shape, generator=g)
+    sd["lin4.weight_v"][:, 217 + 3:] += 0.05 * torch.randn(sd["lin4.weight_v"][:, 217 + 3:].shape, generator=g)
+    node.implicit_network.load_state_dict(sd, strict=True)
+    node.sync_weights()
     node.barf_weights = w.to(s["dev"]).contiguous()
     try:
         out = node.implicit_network(x.to(s["dev"]), None)
@@ -144,10 +183,12 @@ def test_sdf_eval_barf_weights(setup, ctx):
         ctx.check()
     finally:
         node.barf_weights = None
+        node.implicit_network.load_state_dict(sd0, strict=True)
+        node.sync_weights()
     xg = x[0].clone().requires_grad_(True)
-    ref = O.sdf_mlp(xg, s["sc"].sdf_state["object"], None, w)
+    ref = O.sdf_mlp(xg, sd, None, w)
     gref = torch.autograd.grad(ref[:, 0].sum(), xg)[0]
-    plain = O.sdf_mlp(x[0], s["sc"].sdf_state["object"], None, None)
+    plain = O.sdf_mlp(x[0], sd, None, None)
     assert (plain[:, 0] - ref[:, 0]).abs().max().item() > 1e-3, "the mask must change the result for this to test anything"
     close(out[0, :, 0], ref[:, 0], TOL, "object.sdf (BARF)")
     close(out[0, :, 1:], ref[:, 1:], TOL, "object.feat (BARF)")

@@ -27,7 +27,7 @@ def timed(fn, n=3):
 
 # ---------------------------------------------------------------- 1. error vs float64
 print("== 1. tcgen05 SDF chains vs float64 (c = accumulator compensation, scale 1 + c 2^-24)")
-for perturb in (0.0, 0.02):
+for perturb in (0.0, 0.02, 0.05):
     sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), seed=4, perturb=perturb)
     net = scene_io.build_net(sc, ctx, capi.MLP_TC)
     g = torch.Generator().manual_seed(9)
@@ -39,9 +39,11 @@ for perturb in (0.0, 0.02):
         gref = torch.autograd.grad(ref[:, 0].sum(), xg)[0].detach()
         ref = ref.detach()
         near = ref[:, 0].abs() < 0.05
+        if not near.any():
+            near = ref[:, 0].abs() <= ref[:, 0].abs().kthvalue(200).values
         node = net.nodes[nid]
         xd = x.to(dev).contiguous()
-        for c in (0, 6, 12, 18, 24, 32, 48):
+        for c in (0, 8, 10, 11, 12, 14):
             assert L.hold_debug_set(ctx.h, 2, c) == 0
             s0 = torch.empty(x.shape[0], device=dev)
             capi.check(L.hold_sdf_eval(ctx.h, node.slot, x.shape[0], capi.ptr(xd), None, capi.ptr(s0), None, None, capi.stream_ptr()))
@@ -53,7 +55,7 @@ for perturb in (0.0, 0.02):
             ef = (f1.cpu().double() - ref[:, 1:]).abs().max().item() / ref[:, 1:].abs().max().item()
             print(f"perturb {perturb} {nid:6s} c={c:2d}: sdf-only mean {e0.mean().item():+.2e} max {e0.abs().max().item():.2e} near-surface max {e0[near].abs().max().item():.2e} | "
                   f"rev sdf mean {e1.mean().item():+.2e} max {e1.abs().max().item():.2e} | grad rel {eg:.2e} feat rel {ef:.2e}", flush=True)
-        L.hold_debug_set(ctx.h, 2, 0)
+        L.hold_debug_set(ctx.h, 2, -1)
 
 # ---------------------------------------------------------------- 2. kernel times
 print("== 2. kernel times")
