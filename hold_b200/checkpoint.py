@@ -99,7 +99,7 @@ def load_reference_state_dict(net, sd: dict, prefix: str = "model.", strict: boo
     # ObjectModel buffers: not parameters of the mirror, but they decide the object's transform (obj_tfs, verts)
     for nid, bufs in object_model_buffers(sd, prefix).items():
         node = net.nodes[nid] if nid in net.nodes else None
-        if node is None or not hasattr(node.server, "set_object_model"):
+        if node is None or not hasattr(getattr(node, "server", None), "set_object_model"):
             continue
         if "v3d_cano" in bufs and tuple(bufs["v3d_cano"].shape) != tuple(node.server.v3d_cano.shape) and strict:
             raise KeyError(f"nodes.{nid}.server.object_model.v3d_cano is {tuple(bufs['v3d_cano'].shape)}, the mirror holds "

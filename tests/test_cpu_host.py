@@ -145,6 +145,23 @@ def test_reference_checkpoint_key_mapping():
         assert torch.equal(a, b), k
     p = dst.nodes["right"].params(torch.tensor([0, 3]))
     assert set(p) == {"right.global_orient", "right.pose", "right.transl", "right.betas"} and p["right.betas"].shape == (2, 10)
+    # ObjectModel buffers (model/obj/object_model.py:23-27) reach the object server's set_object_model
+    class FakeServer:
+        def __init__(self):
+            self.v3d_cano, self.got = torch.zeros(10, 3), None
+
+        def set_object_model(self, obj_scale=None, norm_mat=None, v3d_cano=None):
+            self.got = dict(obj_scale=obj_scale, norm_mat=norm_mat, v3d_cano=v3d_cano)
+
+    dst2 = FakeNet()
+    object.__setattr__(dst2.nodes["object"], "server", FakeServer())
+    sd["model.nodes.object.server.object_model.obj_scale"] = torch.tensor([0.83])
+    sd["model.nodes.object.server.object_model.norm_mat"] = torch.eye(4) * 2.0
+    sd["model.nodes.object.server.object_model.denorm_mat"] = torch.eye(4) * 0.5
+    ck.load_reference_state_dict(dst2, sd)
+    got = dst2.nodes["object"].server.got
+    assert got is not None and float(got["obj_scale"]) == pytest.approx(0.83) and got["norm_mat"][0, 0] == 2.0 and got["v3d_cano"].shape == (10, 3)
     del sd["model.nodes.right.density.beta"]
     with pytest.raises(KeyError):
         ck.load_reference_state_dict(FakeNet(), sd)
+
