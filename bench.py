@@ -116,6 +116,19 @@ def _cpu_worker(rank, n_workers, threads, n_rays, repeats, barrier, q):
     q.put((rank, time.perf_counter() - t0))
 
 
+def usable_cpus() -> int:
+    """Hardware threads this process may actually use: scheduler affinity, capped by the cgroup CPU quota (a container on a
+    128-thread host may own far fewer; os.cpu_count() does not know)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_rays_per_s(n_rays_per_worker: int = 1024, repeats: int = 1, threads: int | None = None, workers: int | None = None):
     """The reference's algorithm (oracle port, pinned to the reference modules by oracle/ref_harness.py) on ALL host cores:
     rays are independent, so the frame's 512-ray chunks (datasets/eval_datasets.py:13) are farmed over `workers` processes of
@@ -123,7 +136,7 @@ def cpu_reference_rays_per_s(n_rays_per_worker: int = 1024, repeats: int = 1, th
     8562Y+: 16 threads 105 rays/s, 32: 89, 64: 56, 128: 0.84).  Wall clock from a common start barrier to the last worker's end."""
     import multiprocessing as mp
 
-    ncpu = os.cpu_count() or 1
+    ncpu = usable_cpus()
     threads = threads or int(os.environ.get("HOLD_CPU_THREADS", min(16, ncpu)))
     workers = workers or int(os.environ.get("HOLD_CPU_WORKERS", max(1, ncpu // threads)))
     ctx = mp.get_context("spawn")
@@ -138,14 +151,14 @@ def cpu_reference_rays_per_s(n_rays_per_worker: int = 1024, repeats: int = 1, th
     for p_ in procs:
         p_.join()
     total = n_rays_per_worker * workers * repeats
-    return total / dt, threads * workers, dt, dict(workers=workers, threads_per_worker=threads, rays=total,
-                                                    slowest_worker_s=max(d for _, d in done))
+    return total / dt, threads * workers, dt, dict(workers=workers, threads_per_worker=threads, rays=total, usable_cpus=ncpu,
+                                                    os_cpu_count=os.cpu_count(), slowest_worker_s=max(d for _, d in done))
 
 
 def _cpu_line(rps, cores, dt, info, steps):
     return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{info['rays']} rays of the same 512x512 workload ({info['workers']} processes x {info['threads_per_worker']} threads, "
-                      f"disjoint 512-ray chunks, {steps} pass(es)) in {dt:.1f} s wall; oracle/hold_oracle.py = torch-CPU fp32 restatement pinned "
+                      f"disjoint 512-ray chunks, {steps} pass(es); {info.get('usable_cpus')} usable hardware threads of {info.get('os_cpu_count')}) in {dt:.1f} s wall; oracle/hold_oracle.py = torch-CPU fp32 restatement pinned "
                       f"to the reference's own modules (oracle/ref_harness.py; /root/reference cannot travel to the GPU box, hence 'port')"}
 
 
@@ -195,6 +208,84 @@ def ncu_traffic_bytes():
     return None, None
 
 
+def run_train(args):
+    """SURVEY C5 / BASELINE configs[4]: one training step = 10 frames x 128 pixels per rank (parser.py:26,87-89) through sampler ->
+    nodes in training mode (forward + backward incl. the second-order path) -> merge + integrate -> losses -> ONE flat-bucket
+    all-reduce of every gradient -> Adam.  Prints its own JSON line (metric: training rays/s); weak scaling (rays per rank fixed)."""
+    import __graft_entry__ as g
+
+    rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from hold_b200 import capi, scene_io, synth, train
+
+    ctx = capi.Context(local_rank)
+    Bf, px = 10, 128
+    sc = synth.make_scene(H=H, W=W, S=S, nodes=NODES, B=Bf, seed=0)
+    for nid in sc.node_ids:
+        sc.beta[nid] = torch.tensor(BETA)
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    gen = torch.Generator().manual_seed(100 + rank)
+    ids = torch.stack([torch.randperm(H * W, generator=gen)[:px] for _ in range(Bf)])          # this rank's pixels of every frame
+    inp = scene_io.scene_input(sc, dev)
+    inp["uv"] = torch.gather(inp["uv"], 1, ids.to(dev)[:, :, None].expand(-1, -1, 2)).contiguous()
+    pose_leaves = []
+    for k in list(inp):   # per-frame poses as leaves: the step differentiates through inverse skinning and the pose servers
+        if torch.is_tensor(inp[k]) and inp[k].is_floating_point() and any(k.endswith(sfx) for sfx in (".full_pose", ".transl", ".global_orient")):
+            inp[k] = inp[k].clone().requires_grad_(True)
+            pose_leaves.append(inp[k])
+    R = Bf * px
+    gt_rgb = torch.rand(R, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    gt_mask = torch.zeros(R, 4, device=dev)
+    gt_mask[:, 0] = 1.0
+    ts = train.TrainStep(net, group=None)
+    ts.params = ts.params + pose_leaves          # pose gradients ride in the same flat bucket
+    n_grad = sum(p.numel() for p in ts.params)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        loss, parts = ts.step(inp, gt_rgb, gt_mask)
+    sync_all()
+    ctx.check()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    e0.record()
+    for _ in range(args.steps):
+        loss, parts = ts.step(inp, gt_rgb, gt_mask)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training rays/sec (forward + backward + gradient all-reduce + Adam)", "value": world * R * args.steps / (ms * 1e-3),
+            "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[4] / SURVEY C5: training step, {Bf} frames x {px} pixels per rank, right hand + object, 128 samples/ray, beta {BETA}",
+                       "collective": f"one flat-bucket all-reduce of {n_grad} fp32 gradients per step (NCCL)" if world > 1 else "none (1 rank)",
+                       "losses": "L1 rgb + L2 semantics + eikonal (256 canonical samples per frame)", "mlp_mode": "tcgen05 fp16-split x3 (hold_linear) + cuBLAS fp32 weight-gradient GEMMs"},
+            "gpu_launches": ctx.launches - l0, "loss": float(loss), "loss_terms": {k: float(v) for k, v in parts.items()}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,9 +294,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("HOLD_MLP_MODE", "auto"), choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="render", choices=["render", "train"],
+                    help="render: BASELINE configs[1] (the driver's line); train: one data-parallel training step (configs[4] / SURVEY C5)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] (two hands + object) and full-forward (with background) fields")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "train":
+        return run_train(args)
 
     import __graft_entry__ as g
 
@@ -332,7 +428,7 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rps, cores, dt, info = cpu_reference_rays_per_s(1024, repeats=1)
+        rps, cores, dt, info = cpu_reference_rays_per_s(512, repeats=1)
         cpu = _cpu_line(rps, cores, dt, info, 1)
     line = {
         "metric": "rays/sec (128 samples/ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,

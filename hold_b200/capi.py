@@ -51,6 +51,11 @@ class RenderOut(C.Structure):
                 ("fg_weights", fp)]
 
 
+class EwArgs(C.Structure):
+    _fields_ = [("in0", fp), ("in1", fp), ("in2", fp), ("out0", fp), ("out1", fp), ("ld_in0", C.c_int32), ("ld_in1", C.c_int32),
+                ("ld_in2", C.c_int32), ("ld_out0", C.c_int32), ("ld_out1", C.c_int32), ("ncols", C.c_int32), ("aux", C.c_int32)]
+
+
 class SamplerRand(C.Structure):
     _fields_ = [("jitter", fp), ("u", fp), ("extra_idx", fp)]
 
@@ -86,6 +91,8 @@ EXPORTS = {
     "hold_bg_set_weights": (C.c_int, [C.c_void_p, C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.c_int, C.c_void_p]),
     "hold_background": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, fp, fp, C.c_void_p]),
     "hold_sdf_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_void_p]),
+    "hold_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]),
+    "hold_train_ew": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(EwArgs), C.c_void_p]),
     "hold_rgb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, C.c_void_p]),
     "hold_forward_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.POINTER(NodePose), fp, fp, fp, C.c_void_p]),
     "hold_inverse_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.POINTER(NodePose), fp, fp, fp, C.c_void_p]),

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <new>
+#include <algorithm>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -16,6 +17,7 @@
 #include "mesh_sdf.cuh"
 #include "mise.cuh"
 #include "warp_bwd.cuh"
+#include "train.cuh"
 
 namespace hold {
 
@@ -617,7 +619,13 @@ int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_lo
   const int max_pts = 1 << 20;
   const int rays_per_chunk = max(1, min(rpf, max_pts / S));
   const size_t cp = (size_t)rays_per_chunk * S;
-  WS(WS_XC, float, cp * 3 > (size_t)0 ? cp * 3 : 1, xc_ws);
+  // canonical points of the WHOLE call in one launch (full grid, one vertex-group setup per block instead of one per 1 Mi-point
+  // chunk: the per-chunk launches of round 1 ran at 0.57 waves); the MLP stages below are chunked for their 1 GB feature buffer
+  float* xc_all = out->canonical_pts;
+  if (xc_all == nullptr) {
+    WS(WS_XC, float, (size_t)R * S * 3, xc_ws);
+    xc_all = xc_ws;
+  }
   WS(WS_SSDF, float, cp, sdf_ws);
   WS(WS_GRAD, float, cp * 3, grad_ws);
   WS(WS_FEAT, float, cp * kFeat, feat_ws);
@@ -631,6 +639,8 @@ int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_lo
     // RenderingNet with a 45-dim pose of zeros still applies lin_pose: embed = bias (texture_net.py:80-82)
     HOLD_REQUIRE(false, "hand node needs pose_cond (pass zeros for the first 20 training epochs)");
   }
+  rc = launch_inverse_warp(ctx, ns, B, rpf * S, true, S, S, out->z_vals, cam_loc, ray_dirs, nullptr, pose, xc_all, nullptr, nullptr, nullptr, s);
+  if (rc) return rc;
   for (int b = 0; b < B; ++b) {
     hold_node_pose pb = *pose;
     pb.tfs = pose->tfs + (size_t)b * (hand ? kJoints * 16 : 16);
@@ -639,11 +649,8 @@ int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_lo
       const int rc_n = min(rays_per_chunk, rpf - r0);
       const size_t ray0 = (size_t)b * rpf + r0;
       const int P = rc_n * S;
-      float* xc = out->canonical_pts ? out->canonical_pts + ray0 * S * 3 : xc_ws;
+      float* xc = xc_all + ray0 * S * 3;
       float* sdf = out->sdf ? out->sdf + ray0 * S : sdf_ws;
-      rc = launch_inverse_warp(ctx, ns, 1, P, true, S, S, out->z_vals + ray0 * S, cam_loc + ray0 * 3, ray_dirs + ray0 * 3,
-                               nullptr, &pb, xc, nullptr, nullptr, nullptr, s);
-      if (rc) return rc;
       rc = launch_sdf(ctx, ns, P, xc, pose->embed_w, sdf, grad_ws, feat_ws, nullptr, s);
       if (rc) return rc;
       dim3 grid(ceil_div(P, 128), 1);
@@ -1011,6 +1018,35 @@ int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c, const float*
   HOLD_REQUIRE(x_c && sdf, "NULL argument");
   HOLD_REQUIRE((grad == nullptr) == (feat == nullptr), "grad and feat must be requested together");
   return launch_sdf(ctx, ctx->nodes[node], P, x_c, embed_w, sdf, grad, feat, nullptr, (cudaStream_t)stream);
+}
+
+int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda, int kvalid, int add_bias, const float* in_scale,
+                float* C, int ldc, int nvalid, void* stream) {
+  int rc = check_node(ctx, node, true);
+  if (rc) return rc;
+  HOLD_REQUIRE(P >= 0, "negative P");
+  if (P == 0) return HOLD_OK;
+  HOLD_REQUIRE(A && C, "NULL argument");
+  NodeState& ns = ctx->nodes[node];
+  HOLD_REQUIRE(ns.tc != nullptr, "hold_linear needs the packed tcgen05 weight images (hold_node_set_weights)");
+  return tc_launch_linear(ctx, ns, mat, P, A, lda, kvalid, add_bias, in_scale, C, ldc, nvalid, (cudaStream_t)stream);
+}
+
+int hold_train_ew(hold_ctx* ctx, int op, int P, const hold_ew_args* args, void* stream) {
+  HOLD_REQUIRE(ctx && args, "NULL argument");
+  HOLD_REQUIRE(op >= 0 && op <= EW_RELU_BWD && P >= 0, "bad op / P");
+  if (P == 0) return HOLD_OK;
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  EwArgs a;
+  a.in0 = args->in0, a.in1 = args->in1, a.in2 = args->in2, a.out0 = args->out0, a.out1 = args->out1;
+  a.ld_in0 = args->ld_in0, a.ld_in1 = args->ld_in1, a.ld_in2 = args->ld_in2, a.ld_out0 = args->ld_out0, a.ld_out1 = args->ld_out1;
+  a.ncols = args->ncols, a.aux = args->aux;
+  HOLD_REQUIRE(a.ncols >= 1 && a.ncols <= 320 && a.in0 && a.out0, "bad elementwise arguments");
+  const size_t total = (size_t)P * (size_t)a.ncols;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+  k_train_ew<<<blocks, 256, 0, (cudaStream_t)stream>>>(op, P, a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
 }
 
 int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const float* normals, const float* pose_cond,

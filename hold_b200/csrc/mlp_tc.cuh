@@ -59,7 +59,8 @@ __global__ void k_scale_vec(const float* __restrict__ src, int n, float c, float
 struct TcMlp {
   uint8_t* sdf_img[HOLD_MAX_LAYERS] = {nullptr};
   uint8_t* rgb_img[HOLD_MAX_LAYERS] = {nullptr};
-  uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient
+  uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient, 8: feature rows (training)
+  uint8_t* rgb_imgT[6] = {nullptr};                // training backward: [0] W_0^T feature part, [1] W_0^T other inputs, [2..4] W_1..3^T
   int sdf_nst[HOLD_MAX_LAYERS], rgb_nst[HOLD_MAX_LAYERS];
 };
 
@@ -86,6 +87,12 @@ struct TcArgs {
   const float* frame_code;
   float r_sphere;
   float unscale;             // accumulator -> value: kTcUnscale (times the experimental compensation factor, hold_debug_set key 2)
+  // MLP_LINEAR (hold_linear): C[P, nvalid] = A[P, kvalid] . W^T (+ bias): one layer against one packed image
+  const float* lin_in;
+  float* lin_out;
+  const float* in_scale;     // device scalar s (a power of two) or NULL: A is fed as A / s, C comes out times s (keeps tiny gradients
+                             // inside the fp16 hi/lo split's range)
+  int lda, ldc, kvalid, nvalid;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -292,9 +299,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 template <int MODE>
 struct TcCfg {
   static constexpr bool kColorLike = (MODE == MLP_COLOR || MODE == MLP_BG_RGB);   // ReLU chain with a 3-row sigmoid head
-  static constexpr int kAChunks = kColorLike ? 5 : 4;   // 64-wide SW128 A chunks in smem
+  static constexpr bool kWide = kColorLike || MODE == MLP_LINEAR;                  // first operand up to 320 wide
+  static constexpr int kAChunks = kWide ? 5 : 4;   // 64-wide SW128 A chunks in smem
   static constexpr int kHandoffs = 2 * kAChunks;                 // 32-wide epilogue->MMA hand-offs
-  static constexpr int kStages = kColorLike ? 2 : 3;
+  static constexpr int kStages = kWide ? 2 : 3;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
   static constexpr int kSmemW = kStages * kTcStageBytes;
   static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
@@ -302,7 +310,7 @@ struct TcCfg {
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
-  static_assert(MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV || MODE == MLP_COLOR || MODE == MLP_BG_SDF || MODE == MLP_BG_RGB, "chains built on tcgen05");
+  static_assert(MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV || MODE == MLP_COLOR || MODE == MLP_BG_SDF || MODE == MLP_BG_RGB || MODE == MLP_LINEAR, "chains built on tcgen05");
   if (a.st != nullptr && a.st->done) return;
   using Cfg = TcCfg<MODE>;
   constexpr bool kColorLike = Cfg::kColorLike;
@@ -413,7 +421,31 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       const bool valid = p < a.P;
       float px = 0.f, py = 0.f, pz = 0.f, pw = 0.f;
       // ---------------------------------------------------------- prologue: layer-0 A operand (this warp's columns)
-      if (MODE == MLP_BG_SDF) {
+      if (MODE == MLP_LINEAR) {
+        // rows of a [P, lda] fp32 matrix, columns [0, kvalid) (zero padded to the image's K), optionally divided by *in_scale
+        const float isc = (a.in_scale != nullptr) ? kTcScaleA / __ldg(a.in_scale) : kTcScaleA;
+        const float* src = a.lin_in + (size_t)p * a.lda;
+        const int nst = a.L[0].nst;
+        for (int h = 0; h < nst; ++h) {
+          const int k0 = h * 32 + sub * 8;
+          float x[8];
+          if (valid && k0 + 8 <= a.kvalid) {
+            const float4 f0 = __ldg(reinterpret_cast<const float4*>(src + k0)), f1 = __ldg(reinterpret_cast<const float4*>(src + k0) + 1);
+            x[0] = f0.x, x[1] = f0.y, x[2] = f0.z, x[3] = f0.w, x[4] = f1.x, x[5] = f1.y, x[6] = f1.z, x[7] = f1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (valid && k0 + i < a.kvalid) ? __ldg(src + k0 + i) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] *= isc;
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int c = h >> 1, j = (h & 1) * 4 + sub;
+          *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
+          *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
+          handoff_arrive(bAReady + 8 * h, lane);
+        }
+      } else if (MODE == MLP_BG_SDF) {
         // inverted-sphere point of sample p % 32 of ray p / 32 (background.py:63-68,102-135), PE-10 + frame code: 116 -> 128
         if (valid) {
           const int ray = p / kBgN;
@@ -500,6 +532,44 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
       }
       // ---------------------------------------------------------- per-layer epilogues
       float head0 = 0.f, head1 = 0.f, head2 = 0.f, gz_acc = 0.f;
+      if (MODE == MLP_LINEAR) {
+        // ======== one layer: C = acc * unscale (* in_scale) + bias, fp32 rows of [P, ldc], columns [0, nvalid) ========
+        const float* bias = a.L[0].bias;
+        const float osc = (a.in_scale != nullptr) ? a.unscale * __ldg(a.in_scale) : a.unscale;
+        if (!mbar_wait(bDFull, d_par & 1, a.err, 4, abort_flag)) break;
+        d_par ^= 1u;
+        tc_fence_after();
+        const uint32_t t_col = t_lane + (uint32_t)(sub * 8);
+        uint32_t raw[8];
+        tc_ld8(t_col, raw);
+        float* dst = a.lin_out + (size_t)p * a.ldc;
+#pragma unroll 2
+        for (int h = 0; h < 8; ++h) {
+          const int n0 = h * 32 + sub * 8;
+          tc_wait_ld();
+          float out[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) out[i] = __uint_as_float(raw[i]) * osc;
+          if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
+          if (bias != nullptr && n0 < a.nvalid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[i] += (n0 + i < a.nvalid) ? __ldg(bias + n0 + i) : 0.f;
+          }
+          if (valid) {
+            if (n0 + 8 <= a.nvalid) {
+              *reinterpret_cast<float4*>(dst + n0) = make_float4(out[0], out[1], out[2], out[3]);
+              *reinterpret_cast<float4*>(dst + n0 + 4) = make_float4(out[4], out[5], out[6], out[7]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (n0 + i < a.nvalid) dst[n0 + i] = out[i];
+            }
+          }
+        }
+        tc_fence_before();
+        epi_bar();   // every warp has read its accumulator columns before the next tile's MMAs overwrite them
+        continue;
+      }
       if (MODE == MLP_SDF_REV) {
         // ======== reverse-mode gradient: 8 forward layers (stash softplus'), feature layer, 8 backward layers ========
         // d sdf/d z_7 = w_sdf * s_7;  d sdf/d z_{l-1} = (g_l . W_l) * s_{l-1};  embedding columns (skip input of
@@ -817,21 +887,27 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
 }
 
 // Transposed image for the reverse-mode gradient: B rows = input index k_in of layer l, K = output index n_out:
-// WT[k_in][n_out] = kTcScaleW * scale * fold(v, g)[n_out][k_in]  (zero outside [N_out) x [K_in)).
-__global__ void k_tc_pack_T(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int N_out, int K_in,
-                            float scale, uint8_t* __restrict__ img) {
+// WT[r][n_out] = kTcScaleW * scale * fold(v, g)[row_off + n_out][src(r)]  (zero outside [N_out) x valid sources).
+// colmap: 0: src = r (r < K_in);  1: colour lin0, feature part: src = 14 + r (r < 256);
+//         2: colour lin0, other inputs in the A operand's order [x_c, n, pose (14) | time code (32)]: src = r (r < 14), 256 + r (r < K_in - 256)
+__global__ void k_tc_pack_T(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N_out, int K_in,
+                            int colmap, float scale, uint8_t* __restrict__ img) {
   const int r = blockIdx.x;   // k_in, 0..255
   const int n = threadIdx.x;  // n_out, 0..255
+  int src = -1;
+  if (colmap == 0) src = (r < K_in) ? r : -1;
+  else if (colmap == 1) src = 14 + r;
+  else src = (r < 14) ? r : ((256 + r < K_in) ? 256 + r : -1);
   float w = 0.f;
-  if (n < N_out && r < K_in) {
-    const float* vr = v + (size_t)n * in_dim;
+  if (n < N_out && src >= 0) {
+    const float* vr = v + (size_t)(row_off + n) * in_dim;
     float f = 1.0f;
     if (g != nullptr) {
       float ss = 0.f;
       for (int k = 0; k < in_dim; ++k) ss += vr[k] * vr[k];
-      f = g[n] / sqrtf(ss);
+      f = g[row_off + n] / sqrtf(ss);
     }
-    w = kTcScaleW * (scale * (vr[r] * f));
+    w = kTcScaleW * (scale * (vr[src] * f));
   }
   const __half h = __float2half_rn(w);
   const __half l = __float2half_rn(w - __half2float(h));
@@ -846,6 +922,7 @@ static int tc_init(hold_ctx*) {
   e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_ONLY>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_COLOR>::kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_SDF_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_SDF_REV>::kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_tc<MLP_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<MLP_LINEAR>::kSmemBytes);
   if (e != cudaSuccess) { set_error("tcgen05 kernel attribute: %s", cudaGetErrorString(e)); return HOLD_E_CUDA; }
   return HOLD_OK;
 }
@@ -856,6 +933,7 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->sdf_img[l]) cudaFree(ns.tc->sdf_img[l]);
     if (ns.tc->rgb_img[l]) cudaFree(ns.tc->rgb_img[l]);
     if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
+    if (l < 6 && ns.tc->rgb_imgT[l]) cudaFree(ns.tc->rgb_imgT[l]);
   }
   delete ns.tc;
   ns.tc = nullptr;
@@ -874,11 +952,18 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     k_tc_pack<<<256, 128, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], row_off, N, K, kpad, scale, 0, t.sdf_img[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
-  for (int l = 0; l < 8; ++l) {  // W_l^T for the reverse-mode gradient (layers 7..0)
+  for (int l = 0; l < 9; ++l) {  // W_l^T for the reverse-mode gradient (layers 7..0); l = 8: the feature rows (training backward)
     const int K_in = (l == 0) ? kEmbed : kHidden, N_out = (l == 3) ? kHidden - kEmbed : kHidden;
     if (!t.sdf_imgT[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgT[l], (size_t)8 * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
-    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], N_out, K_in, scale, t.sdf_imgT[l]);
+    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], l == 8 ? 1 : 0, N_out, K_in, 0, scale, t.sdf_imgT[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  for (int i = 0; i < 5; ++i) {  // colour net transposes for the training backward: lin0 in two parts (its K = 320 > 256), lin1..3
+    const int l = (i < 2) ? 0 : i - 1;
+    if (!t.rgb_imgT[i]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_imgT[i], (size_t)8 * kTcStageBytes));
+    k_tc_pack_T<<<256, 256, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, rgb->in_dim[l], i == 0 ? 1 : (i == 1 ? 2 : 0), 1.0f,
+                                    t.rgb_imgT[i]);
     HOLD_LAUNCH_CHECK(ctx);
   }
   for (int l = 0; l < 4; ++l) {
@@ -919,6 +1004,32 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   } else {
     k_mlp_tc<MLP_SDF_ONLY><<<grid, kTcThreadsTotal, TcCfg<MLP_SDF_ONLY>::kSmemBytes, s>>>(a);
   }
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+// hold_linear: C[P, nvalid] = A[P, kvalid] . M^T (+ bias) for one packed matrix M of the node (see include/hold_b200.h for `mat`)
+static int tc_launch_linear(hold_ctx* ctx, NodeState& ns, int mat, int P, const float* A, int lda, int kvalid, int add_bias,
+                            const float* in_scale, float* Cout, int ldc, int nvalid, cudaStream_t s) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = P, a.n_layers = 1;
+  const uint8_t* img = nullptr;
+  const float* bias = nullptr;
+  int nst = 8, kmax = 256, nmax = 256;
+  if (mat >= 0 && mat <= 8) { img = ns.tc->sdf_img[mat]; bias = ns.sdf.bias[mat]; nst = ns.tc->sdf_nst[mat]; kmax = (mat == 0) ? kEmbed : 256; nmax = ns.sdf.N[mat]; }
+  else if (mat >= 16 && mat <= 24) { img = ns.tc->sdf_imgT[mat - 16]; kmax = (mat - 16 == 3) ? kHidden - kEmbed : 256; nmax = (mat == 16) ? kEmbed : 256; }
+  else if (mat >= 32 && mat <= 35) { img = ns.tc->rgb_img[mat - 32]; bias = ns.rgb.bias[mat - 32]; nst = ns.tc->rgb_nst[mat - 32]; kmax = (mat == 32) ? 320 : 256; }
+  else if (mat >= 48 && mat <= 52) { img = ns.tc->rgb_imgT[mat - 48]; nmax = (mat == 49) ? 64 : 256; }
+  HOLD_REQUIRE(img != nullptr, "hold_linear: unknown matrix id %d", mat);
+  HOLD_REQUIRE(kvalid >= 1 && kvalid <= kmax && nvalid >= 1 && nvalid <= nmax, "hold_linear(%d): kvalid %d (max %d) / nvalid %d (max %d)", mat, kvalid, kmax, nvalid, nmax);
+  HOLD_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Cout & 15) == 0, "hold_linear: rows must be 16-byte aligned");
+  HOLD_REQUIRE(!add_bias || bias != nullptr, "hold_linear(%d): this matrix has no bias", mat);
+  a.L[0].wimg = img, a.L[0].bias = add_bias ? bias : nullptr, a.L[0].nst = nst, a.L[0].N = nvalid;
+  a.lin_in = A, a.lda = lda, a.kvalid = kvalid, a.lin_out = Cout, a.ldc = ldc, a.nvalid = nvalid, a.in_scale = in_scale;
+  a.err = ctx->dev_err, a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));
+  const int tiles = ceil_div(P, kTcRows);
+  k_mlp_tc<MLP_LINEAR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_LINEAR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

@@ -90,9 +90,33 @@ def node_sdf_func(ctx, node):
     return f
 
 
-def generate_mesh(ctx, func, verts, level_set=0.0, res_init=32, res_up=3):
-    """utils/meshing.py:9-72 -> (verts [n,3], faces [m,3], normals, values); marching cubes by skimage on the host and the
-    largest-component selection by trimesh, both optional imports exactly as in the reference."""
+def largest_component(verts, faces):
+    """The reference keeps the connected component of largest surface area (utils/meshing.py:58-70: trimesh.split(only_watertight=
+    False) + argmax of `area`).  Same selection with scipy's connected components over the face-adjacency-by-shared-vertex graph
+    (what trimesh.split uses for only_watertight=False); returns (verts, faces) re-indexed to the kept component."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+
+    f = np.asarray(faces, dtype=np.int64)
+    nv = int(verts.shape[0])
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0)
+    g = sp.coo_matrix((np.ones(e.shape[0], np.int8), (e[:, 0], e[:, 1])), shape=(nv, nv))
+    _, label = connected_components(g, directed=False)
+    fl = label[f[:, 0]]
+    tri = verts[f]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    per = np.bincount(fl, weights=area)
+    keep_f = fl == int(np.argmax(per))
+    used = np.unique(f[keep_f])
+    remap = -np.ones(nv, np.int64)
+    remap[used] = np.arange(used.shape[0])
+    return verts[used], remap[f[keep_f]]
+
+
+def generate_mesh(ctx, func, verts, level_set=0.0, res_init=32, res_up=3, keep_largest=True):
+    """utils/meshing.py:9-72 -> (verts [n,3], faces [m,3]) of the largest connected component (keep_largest=False: the raw
+    marching-cubes tuple (verts, faces, normals, values)).  Marching cubes by skimage on the host, an optional import exactly as in
+    the reference; the component selection (trimesh in the reference) is `largest_component` above."""
     from skimage import measure   # noqa: the reference's own dependency for this step
 
     grid, res, gt_scale, gt_center = generate_grid(ctx, func, verts, level_set, res_init, res_up)
@@ -100,4 +124,7 @@ def generate_mesh(ctx, func, verts, level_set=0.0, res_init=32, res_up=3):
     verts_mc, faces, normals, values = mc(volume=grid, gradient_direction="ascent", level=level_set)
     verts_mc = (verts_mc / res - 0.5) * 1.1
     verts_mc = verts_mc * gt_scale + gt_center
-    return verts_mc, faces[:, [0, 2, 1]], normals, values
+    faces = faces[:, [0, 2, 1]]
+    if not keep_largest:
+        return verts_mc, faces, normals, values
+    return largest_component(verts_mc, faces)

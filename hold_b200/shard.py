@@ -45,8 +45,16 @@ def allreduce_flat_(tensors, group=None, average: bool = False):
 
 
 def allreduce_grads_(params, group=None, average: bool = False):
-    """`allreduce_flat_` over the `.grad` of parameters (those that have one)."""
-    allreduce_flat_([p.grad for p in params if p.grad is not None], group=group, average=average)
+    """`allreduce_flat_` over the `.grad` of `params` — ALL of them, in the given (rank-invariant) order: a parameter without a
+    gradient on this rank (e.g. a node none of this rank's rays hit) contributes zeros and receives the sum, so that the bucket has
+    the same layout on every rank (ranks that disagreed on which gradients exist would otherwise reduce mismatched buckets)."""
+    import torch
+
+    params = [p for p in params if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    allreduce_flat_([p.grad for p in params], group=group, average=average)
 
 
 def gather_rays(local, n_total: int, rank: int, world: int, align: int = 512, group=None, dst: int = 0):

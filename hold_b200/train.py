@@ -1,0 +1,411 @@
+"""Training-mode forward/backward of a node on the GPU (hold/hold.py:110-137, model/renderables/node.py:49-87,
+engine/volsdf_utils.py:51-147 with `create_graph=is_training`).
+
+torch.autograd.Functions whose forward AND backward run the algebra of hold_b200/train_algo.py on libhold_b200.so:
+  * every product with a weight matrix: `hold_linear` — the tcgen05 split-precision GEMM (k_mlp_tc<MLP_LINEAR>) against the node's
+    packed weight images (forward and transposed);
+  * every pointwise step between them: `hold_train_ew` (hold_b200/csrc/train.cuh);
+  * the weight-gradient reductions dW = D^T A over the points: torch.matmul (a plain library GEMM, fp32, TF32 off);
+  * inverse skinning / rigid warp and the pose servers: the existing kernels and their backward twins (hold_inverse_warp_bwd,
+    hold_mano_lbs_bwd, hold_object_tf_bwd).
+The second-order path of the reference (normals feed the colour net with create_graph=True) needs no double backward here:
+d sdf / d x_c is an OUTPUT of SdfNetFn and its backward takes a seed for it (train_algo.sdf_backward).
+
+What stays in PyTorch on purpose (host code per BASELINE.json north_star: "Host code stays Python/PyTorch for the training loop"):
+weight-norm folding of the parameters, losses, the optimiser; and, in this first version, the per-point 3x3 normal algebra, the
+Laplace density and the n-way merge + volume integration of the 1 280-ray training batch (tiny next to the nets; their fused
+inference kernels exist, their backward twins are the next step: DESIGN.md)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import capi, train_algo as T
+from .capi import EwArgs, NodePose, check, lib, ptr, stream_ptr
+
+EW = dict(ACT=0, MUL=1, MULROW=2, U_DZ2=3, DZ=4, EMBED=5, EMBED_VJP=6, EMBED_JVP=7, RELU=8, RELU_BWD=9)
+
+
+def fold(lin):
+    """weight-norm fold of one layer of the mirror (nn.utils.weight_norm, dim=0), tracked by autograd."""
+    if hasattr(lin, "weight_v"):
+        return lin.weight_v * (lin.weight_g / lin.weight_v.norm(dim=1, keepdim=True))
+    return lin.weight
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "row-major matrix (rows may be strided)"
+    return t.stride(0)
+
+
+def _ew(node, op, P, ncols, in0, in1=None, in2=None, out0=None, out1=None, aux=0, ld2=None):
+    a = EwArgs()
+    a.in0, a.in1, a.in2 = in0.data_ptr(), (in1.data_ptr() if in1 is not None else None), (in2.data_ptr() if in2 is not None else None)
+    a.out0, a.out1 = out0.data_ptr(), (out1.data_ptr() if out1 is not None else None)
+    a.ld_in0 = _ld(in0) if in0.dim() == 2 else 0
+    a.ld_in1 = (_ld(in1) if in1.dim() == 2 else 0) if in1 is not None else 0
+    a.ld_in2 = ((_ld(in2) if in2.dim() == 2 else 0) if in2 is not None else 0) if ld2 is None else ld2
+    a.ld_out0 = _ld(out0)
+    a.ld_out1 = _ld(out1) if out1 is not None else 0
+    a.ncols, a.aux = ncols, aux
+    check(lib().hold_train_ew(node.ctx.h, op, P, C.byref(a), stream_ptr()))
+
+
+class CudaOps:
+    """train_algo backend on libhold_b200.so.  net = "sdf" | "rgb".  Activations live in [P,256] (or [P,320]) row buffers."""
+
+    def __init__(self, node, net, W, b):
+        self.node, self.net, self.W, self.b = node, net, W, b   # W, b: folded fp32 tensors (detached), reference column order
+        self.scaled = False                                       # backward: scale operands by a power of two (hold_linear in_scale)
+        self.hand = node.kind == "hand"
+
+    # ---- products with a weight matrix
+    def _linear(self, mat, A, kvalid, nvalid, bias, out_cols=256):
+        P = A.shape[0]
+        assert A.stride(1) == 1 and A.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0, "hold_linear wants 16-byte aligned rows"
+        out = torch.empty(P, out_cols, device=A.device)
+        sc = None
+        if self.scaled:
+            sc = torch.exp2(torch.floor(torch.log2(A.detach().abs().amax().clamp_min(1e-30)))).reshape(1).float().contiguous()
+        check(lib().hold_linear(self.node.ctx.h, self.node.slot, mat, P, ptr(A) if A.is_contiguous() else C.c_void_p(A.data_ptr()), A.stride(0),
+                                kvalid, 1 if bias else 0, ptr(sc), C.c_void_p(out.data_ptr()), out.stride(0), nvalid, stream_ptr()))
+        return out[:, :nvalid]
+
+    def lin(self, A, l, bias=True):
+        if self.net == "sdf":
+            if l == 8:   # [sdf head | 256 feature rows]: the head is a matrix-vector product
+                feat = self._linear(8, A, 256, 256, bias)
+                head = A @ self.W[8][0] + (self.b[8][0] if bias else 0.0)
+                return torch.cat([head[:, None], feat], 1)
+            n = T.N_SKIP_A if l == 3 else 256
+            return self._linear(l, A, A.shape[1], n, bias)
+        if l == 4:       # 3-row sigmoid head
+            y = A @ self.W[4].T
+            return y + self.b[4] if bias else y
+        if l == 0:       # kernel operand order: [feature (256) | x_c, n, pose (14) | time code (32)]
+            A = torch.cat([A[:, 14:270], A[:, :14], A[:, 270:], A.new_zeros(A.shape[0], 320 - A.shape[1])], 1)
+            return self._linear(32, A, 320, 256, bias)
+        return self._linear(32 + l, A, 256, 256, bias)
+
+    def lin_t(self, A, l):
+        if self.net == "sdf":
+            if l == 8:
+                d_feat = A[:, 1:].contiguous()
+                return A[:, :1] * self.W[8][0][None, :] + self._linear(24, d_feat, 256, 256, False)
+            if l == 0:
+                return self._linear(16, A, 256, T.D_EMBED, False, out_cols=40)
+            return self._linear(16 + l, A, A.shape[1], 256, False)
+        if l == 4:
+            return A @ self.W[4]
+        if l == 0:
+            k0 = self.W[0].shape[1]
+            f = self._linear(48, A, 256, 256, False)
+            o = self._linear(49, A, 256, 64, False, out_cols=64)
+            return torch.cat([o[:, :14], f, o[:, 14:14 + (k0 - 270)]], 1)
+        return self._linear(49 + l, A, 256, 256, False)
+
+    def wgrad(self, D, A):
+        return D.T @ A
+
+    def colsum(self, D):
+        return D.sum(0)
+
+    def w_row(self):
+        return self.W[8][0]
+
+    # ---- pointwise steps: hold_train_ew
+    def act(self, z, e=None):
+        P, n = z.shape
+        a, s = torch.empty(P, 256, device=z.device), torch.empty(P, 256, device=z.device)
+        _ew(self.node, EW["ACT"], P, n, z, e, None, a, s)
+        return (a[:, :n] if e is None else a), s[:, :n]
+
+    def _binary(self, op, x, y, in2=None, ld2=None, two=False):
+        P, n = y.shape
+        o0 = torch.empty(P, 256 if n <= 256 else 320, device=y.device)
+        o1 = torch.empty_like(o0) if two else None
+        _ew(self.node, op, P, n, x, y, in2, o0, o1, ld2=ld2)
+        return (o0[:, :n], o1[:, :n]) if two else o0[:, :n]
+
+    def mul(self, x, y):
+        return self._binary(EW["MUL"], x, y)
+
+    def mulrow(self, row, y):
+        return self._binary(EW["MULROW"], row.contiguous(), y)
+
+    def u_dz2(self, h, s, q):
+        if q.stride(0) == 0:   # q_7 = w broadcast over the points
+            return self._binary(EW["U_DZ2"], h, s, q[0].contiguous(), ld2=0, two=True)
+        return self._binary(EW["U_DZ2"], h, s, q, two=True)
+
+    def dz(self, dA, s, dz2):
+        return self._binary(EW["DZ"], dA, s, dz2)
+
+    def embed(self, x, embed_w, order):
+        P = x.shape[0]
+        out = torch.empty(P, 40, device=x.device)
+        xc = x.contiguous()
+        _ew(self.node, EW["EMBED"], P, 40, xc, embed_w, None, out, aux=order)
+        return out[:, :T.D_EMBED]
+
+    def embed_vjp(self, d1, ge):
+        P = d1.shape[0]
+        out = torch.empty(P, 3, device=d1.device)
+        _ew(self.node, EW["EMBED_VJP"], P, 3, d1, ge, None, out)
+        return out
+
+    def embed_jvp(self, d1, v):
+        P = d1.shape[0]
+        out = torch.empty(P, 40, device=d1.device)
+        _ew(self.node, EW["EMBED_JVP"], P, 40, d1, v.contiguous(), None, out)
+        return out[:, :T.D_EMBED]
+
+    def relu(self, z):
+        P, n = z.shape
+        out = torch.empty(P, 256, device=z.device)
+        _ew(self.node, EW["RELU"], P, n, z, None, None, out)
+        return out[:, :n]
+
+    def relu_bwd(self, dA, a):
+        return self._binary(EW["RELU_BWD"], dA, a)
+
+
+def _folded_sdf(node):
+    W = [fold(getattr(node.implicit_network, f"lin{l}")) for l in range(9)]
+    b = [getattr(node.implicit_network, f"lin{l}").bias for l in range(9)]
+    return W, b
+
+
+def _folded_rgb(node):
+    W = [fold(getattr(node.rendering_network, f"lin{l}")) for l in range(5)]
+    b = [getattr(node.rendering_network, f"lin{l}").bias for l in range(5)]
+    return W, b
+
+
+class SdfNetFn(torch.autograd.Function):
+    """(sdf [P], feat [P,256], g = d sdf / d x_c [P,3]) = ImplicitNet(x_c); differentiable w.r.t. x_c and the folded weights,
+    including through g (the reference's create_graph=True path)."""
+
+    @staticmethod
+    def forward(fctx, node, x, *Wb):
+        fctx.set_materialize_grads(False)
+        W, b = [w.detach().float() for w in Wb[:9]], [v.detach().float() for v in Wb[9:]]
+        Wk = list(W)
+        Wk[0] = W[0][:, :T.D_EMBED].contiguous()     # hand: the 45 pose-condition columns are multiplied by zero (shape_net.py:104-106)
+        ops = CudaOps(node, "sdf", Wk, b)
+        sdf, feat, g, st = T.sdf_forward(ops, x.detach().float().contiguous(), node.embed_w())
+        fctx.ops, fctx.st, fctx.k0 = ops, st, W[0].shape[1]
+        return sdf.contiguous(), feat.contiguous(), g
+
+    @staticmethod
+    def backward(fctx, d_sdf, d_feat, d_g):
+        ops = fctx.ops
+        ops.scaled = True
+        f = lambda t: None if t is None else t.float().contiguous()
+        d_x, dW, db = T.sdf_backward(ops, fctx.st, f(d_sdf), f(d_feat), f(d_g))
+        dW[4] = dW[4] * (1.0 / math.sqrt(2.0))       # the packed W_4 carries the skip's 1/sqrt 2
+        if fctx.k0 > T.D_EMBED:
+            dW[0] = torch.cat([dW[0], dW[0].new_zeros(256, fctx.k0 - T.D_EMBED)], 1)
+        return (None, d_x, *dW, *db)
+
+
+class RgbNetFn(torch.autograd.Function):
+    """rgb [P,3] = RenderingNet([x_c, n, pose_embed, feat (, time)]) (texture_net.py:69-101); differentiable w.r.t. the input
+    matrix and the folded weights."""
+
+    @staticmethod
+    def forward(fctx, node, inp, *Wb):
+        W, b = [w.detach().float() for w in Wb[:5]], [v.detach().float() for v in Wb[5:]]
+        ops = CudaOps(node, "rgb", W, b)
+        rgb, st = T.rgb_forward(ops, inp.detach().float().contiguous())
+        fctx.ops, fctx.st = ops, st
+        return rgb
+
+    @staticmethod
+    def backward(fctx, d_rgb):
+        fctx.ops.scaled = True
+        d_in, dW, db = T.rgb_backward(fctx.ops, fctx.st, d_rgb.float().contiguous())
+        return (None, d_in, *dW, *db)
+
+
+class InverseWarpFn(torch.autograd.Function):
+    """x_c = deformer.forward(x, tfs, inverse=True) (mano/deformer.py:34-68,145-170; obj/deformer.py:10-31); differentiable w.r.t.
+    tfs (skinning weights are detached in the reference, deformer.py:101) and x."""
+
+    @staticmethod
+    def forward(fctx, node, x, tfs, verts):
+        B, P, _ = x.shape
+        dev = x.device
+        pose = NodePose()
+        tf = tfs.detach().float().contiguous()
+        pose.tfs = tf.data_ptr()
+        keep = [tf]
+        hand = node.kind == "hand"
+        if hand:
+            vv = verts.detach().float().contiguous()
+            pose.posed_verts = vv.data_ptr()
+            keep.append(vv)
+        xi = x.detach().float().contiguous()
+        xc = torch.empty(B, P, 3, device=dev)
+        idx = torch.empty(B, P, 15, dtype=torch.int32, device=dev) if hand else None
+        check(lib().hold_inverse_warp(node.ctx.h, node.slot, B, P, ptr(xi), C.byref(pose), ptr(xc), ptr(idx), None, stream_ptr()))
+        fctx.node, fctx.keep, fctx.idx, fctx.xi, fctx.hand = node, keep, idx, xi, hand
+        return xc
+
+    @staticmethod
+    def backward(fctx, g_xc):
+        node, xi = fctx.node, fctx.xi
+        B, P, _ = xi.shape
+        pose = NodePose()
+        pose.tfs = fctx.keep[0].data_ptr()
+        if fctx.hand:
+            pose.posed_verts = fctx.keep[1].data_ptr()
+        g = g_xc.float().contiguous()
+        g_tfs = torch.zeros_like(fctx.keep[0])
+        g_x = torch.empty_like(xi)
+        check(lib().hold_inverse_warp_bwd(node.ctx.h, node.slot, B, P, ptr(xi), C.byref(pose), ptr(fctx.idx), ptr(g), ptr(g_tfs), ptr(g_x), stream_ptr()))
+        return None, g_x, g_tfs, None
+
+
+def laplace_density(sdf, beta):
+    """engine/density.py:21-26."""
+    return (1.0 / beta) * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))
+
+
+def node_forward_train(node, x, tfs, verts, frame_of_point, pose_cond=None, time_code=None, sync=True):
+    """Node.forward after sampling, training mode (node.py:57-87 + volsdf_utils.py:51-147): deformed points x [B,P,3] ->
+    dict(sdf, x_c, feat, grad, normal, color, density), everything differentiable w.r.t. the node's parameters, tfs, beta,
+    the frame / pose codes.  `verts`: posed vertices (hand).  frame_of_point [B*P] long."""
+    if sync:
+        node.sync_weights()
+    B, P, _ = x.shape
+    x_c = InverseWarpFn.apply(node, x, tfs, verts).reshape(B * P, 3)
+    Ws, bs = _folded_sdf(node)
+    sdf, feat, g = SdfNetFn.apply(node, x_c, *Ws, *bs)
+    # J of forward skinning with detached weights (volsdf_utils.py:66-81): sum_j w_j tfs_j[:3,:3]; hand: KNN vs canonical verts
+    if node.kind == "hand":
+        pose = NodePose()
+        tf = tfs.detach().float().contiguous()
+        pose.tfs = tf.data_ptr()
+        idx = torch.empty(B, P, 15, dtype=torch.int32, device=x.device)
+        xd = torch.empty(B, P, 3, device=x.device)
+        check(lib().hold_forward_warp(node.ctx.h, node.slot, B, P, ptr(x_c.detach().reshape(B, P, 3).contiguous()), C.byref(pose), ptr(xd),
+                                      ptr(idx), None, stream_ptr()))
+        cano = node.server.verts_c[0]
+        d2 = ((x_c.detach().reshape(B * P, 1, 3) - cano[idx.reshape(B * P, 15).long()]) ** 2).sum(-1).clamp(max=4.0)
+        conf = torch.softmax(-d2, dim=1)
+        w = (node.server.m["lbs_weights"][idx.reshape(B * P, 15).long()] * conf[..., None]).sum(1)         # [BP,16], detached by construction
+        J = torch.einsum("pn,pnij->pij", w, tfs[frame_of_point][:, :, :3, :3])
+    else:
+        J = tfs.reshape(B, 4, 4)[frame_of_point][:, :3, :3]
+    normal = torch.nn.functional.normalize(torch.einsum("bi,bij->bj", g, torch.linalg.inv(J)), dim=1, eps=1e-6)
+    if node.kind == "hand":
+        pe = node.rendering_network.lin_pose(pose_cond)[frame_of_point]
+        inp = torch.cat([x_c, normal, pe, feat], 1)
+    else:
+        inp = torch.cat([x_c, normal, x_c.new_zeros(B * P, 8), feat, time_code[frame_of_point]], 1)
+    Wr, br = _folded_rgb(node)
+    color = RgbNetFn.apply(node, inp, *Wr, *br)
+    density = laplace_density(sdf, node.density.get_beta())
+    return dict(sdf=sdf, x_c=x_c, feat=feat, grad=g, normal=normal, color=color, density=density)
+
+
+# ------------------------------------------------------------------------------------------------ scene level (hold_net.py:53-108)
+def density2weight(density, z_vals, z_max):
+    """engine/volsdf_utils.py:220-251."""
+    dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], z_max[:, None] - z_vals[:, -1:]], -1)
+    fe = dists * density
+    alpha = 1 - torch.exp(-fe)
+    T = torch.exp(-torch.cumsum(torch.cat([torch.zeros_like(fe[:, :1]), fe], -1), -1))
+    return alpha * T[:, :-1], T[:, -1]
+
+
+def volumetric_render(f):
+    """hold/hold_utils.py:243-271 (training: no fg_rgb.vis)."""
+    w, bg = density2weight(f["density"], f["z_vals"], f["z_max"])
+    integ = lambda v: (v * w[:, :, None]).sum(1)
+    return dict(fg_rgb=integ(f["color"]), fg_weights=w, mask_prob=w.sum(1, keepdim=True).clamp(0, 1), normal=integ(f["normal"]),
+                depth=integ(f["z_vals"][:, :, None]), fg_semantics=integ(f["semantics"]), bg_weights=bg)
+
+
+def merge_factors(fl):
+    """hold/hold_utils.py:76-121: concat on the sample axis, sort by z (stable: lower node first on ties, as the kernels do),
+    drop (n-1) head / n tail entries (the reference's own asymmetry, :115-118), z_max = z_sorted[:, -n]."""
+    n = len(fl)
+    z = torch.cat([f["z_vals"] for f in fl], 1)
+    zs, idx = torch.sort(z, dim=1, stable=True)
+    out = {}
+    for k in ("color", "normal", "semantics"):
+        v = torch.cat([f[k] for f in fl], 1)
+        out[k] = torch.gather(v, 1, idx[:, :, None].expand(-1, -1, v.shape[2]))[:, n - 1: -n]
+    out["density"] = torch.gather(torch.cat([f["density"] for f in fl], 1), 1, idx)[:, n - 1: -n]
+    out["z_vals"] = zs[:, n - 1: -n]
+    out["z_max"] = zs[:, -n]
+    return out
+
+
+class TrainStep:
+    """One data-parallel training step of the foreground model (hold/hold.py:110-137 without the Lightning plumbing): every
+    rank takes its share of the step's rays, runs sampler (no grad) -> nodes in training mode -> merge + integrate -> losses,
+    back-propagates through the kernels above, then ONE all-reduce over a single flat gradient bucket (shard.allreduce_grads_,
+    the only collective of the step: SURVEY §8e) and the optimiser step (Adam, hold.py:79-101).
+    Losses here: L1 rgb, L2 semantics (loss_terms.py:14-21, :60-70) and the eikonal term on uniform canonical samples
+    (volsdf_utils.py:19-48, global branch; loss.py:83-87).  The kaolin-based terms (mano_cano, opacity_sparse) need the
+    canonical meshes; their targets are served by hold_mesh_sdf / hold_off_in_surface (ops.py) and are added by the caller."""
+
+    def __init__(self, net, lr=1e-4, n_eik=256, group=None):
+        self.net, self.group, self.n_eik = net, group, n_eik
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=lr)
+
+    def forward_loss(self, input, gt_rgb, gt_mask, generator=None):
+        from . import ops
+        from .model import ErrorBoundSampler
+
+        net = self.net
+        uv = input["uv"]
+        B, P, _ = uv.shape
+        dev = uv.device
+        dirs, cam = ops.camera_rays(net.ctx, uv, input["extrinsics"], input["intrinsics"])
+        fr = torch.arange(B, device=dev).repeat_interleave(P)
+        factors, eik = [], []
+        for node in net.nodes.values():
+            node.sync_weights()
+            pose, keep, srv, tfs = node.articulate(input)     # servers under autograd when the pose rows require grad
+            with torch.no_grad():
+                z, _ = ErrorBoundSampler(node).get_z_vals(dirs, cam, pose, B)   # eval-mode sampling: training randomness via `rand`
+            S = z.shape[1]
+            x = (cam[:, None, :] + z[:, :, None] * dirs[:, None, :]).reshape(B, P * S, 3)
+            frp = fr.repeat_interleave(S)
+            hand = node.kind == "hand"
+            o = node_forward_train(node, x, srv["tfs"] if hand else tfs, srv["verts"] if hand else None, frp,
+                                   pose_cond=(input[f"{node.node_id}.full_pose"][:, 3:] / math.pi) if hand else None,
+                                   time_code=None if hand else node.frame_latent_encoder(input["idx"]), sync=False)
+            sem = torch.zeros(B * P, S, 4, device=dev)
+            sem[:, :, node.class_id] = 1.0
+            factors.append(dict(color=o["color"].reshape(B * P, S, 3), normal=o["normal"].reshape(B * P, S, 3),
+                                density=o["density"].reshape(B * P, S), semantics=sem, z_vals=z))
+            # eikonal samples: uniform in [-0.3, 0.3]^3 (volsdf_utils.py:38-42), gradient through the same function
+            xs = (torch.rand(B * self.n_eik, 3, device=dev, generator=generator) * 0.6 - 0.3)
+            Ws, bs = _folded_sdf(node)
+            _, _, ge = SdfNetFn.apply(node, xs, *Ws, *bs)
+            eik.append(((ge.norm(2, dim=-1) - 1) ** 2).mean())
+        comp = volumetric_render(merge_factors(factors))
+        valid = gt_rgb.shape[0]
+        loss_rgb = (comp["fg_rgb"] - gt_rgb).abs().sum() / (valid + 1e-6)
+        loss_sem = ((comp["fg_semantics"] - gt_mask) ** 2).mean()
+        loss_eik = sum(eik) * 1e-5
+        return loss_rgb + loss_sem + loss_eik, dict(rgb=loss_rgb.detach(), sem=loss_sem.detach(), eikonal=loss_eik.detach())
+
+    def step(self, input, gt_rgb, gt_mask, generator=None):
+        from . import shard
+
+        self.opt.zero_grad(set_to_none=False)
+        loss, parts = self.forward_loss(input, gt_rgb, gt_mask, generator)
+        loss.backward()
+        shard.allreduce_grads_(self.params, group=self.group, average=True)
+        torch.nn.utils.clip_grad_norm_(self.params, 0.5)      # train.py:30 gradient_clip_val=0.5, after the reduction
+        self.opt.step()
+        return loss.detach(), parts

@@ -252,6 +252,29 @@ int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c /*[P,3]*/, co
  * time_code [B,32] (the reference concatenates it to the features, engine/volsdf_utils.py:133-141).  -> rgb [P,3]. */
 int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const float* normals, const float* pose_cond,
                   const float* feat, const float* time_code, float* rgb, void* stream);
+
+/* ---- building blocks of the training backward (hold/hold.py:110-137; algebra in hold_b200/train_algo.py).
+ * hold_linear: C[P, nvalid] = A[P, kvalid] . M^T (+ bias) in fp32-level arithmetic (tcgen05, fp16 hi/lo split x 3 passes) against one
+ * of the node's packed matrices M, selected by `mat`:
+ *    0..8    SDF W_l (networks/shape_net.py:118-126; W_4 carries the skip's 1/sqrt 2, l = 8: the 256 feature rows), bias b_l
+ *    16..24  SDF W_l^T (A has N_l columns, C has K_l: 39 for l = 0)
+ *    32..35  colour W_l, l = 0..3 (texture_net.py:95-100); l = 0 takes A in the order [feature (256) | x_c, n, pose (14) | time code (32)]
+ *    48, 49  colour W_0^T: to the 256 feature inputs / to the other inputs [x_c, n, pose (14) | time code (32)];  50..52  colour W_1..3^T
+ * A and C rows must be 16-byte aligned (lda, ldc multiples of 4).  in_scale: device scalar (power of two) or NULL — A is fed as
+ * A / in_scale and C multiplied back, which keeps small gradients inside the split's range. */
+int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda, int kvalid, int add_bias, const float* in_scale,
+                float* C, int ldc, int nvalid, void* stream);
+
+/* Pointwise steps of the training backward on [P, ld] fp32 matrices (hold_b200/csrc/train.cuh): op 0 ACT out0 = [softplus(z) | e],
+ * out1 = softplus'(z); 1 MUL; 2 MULROW (in0 = one row); 3 U_DZ2 out0 = h s, out1 = h q softplus''(z); 4 DZ out0 = in0 in1 (+ in2);
+ * 5 EMBED (aux = derivative order 0..2; in1 = BARF weights or NULL); 6 EMBED_VJP; 7 EMBED_JVP; 8 RELU; 9 RELU_BWD. */
+typedef struct hold_ew_args {
+  const float* in0; const float* in1; const float* in2;
+  float* out0; float* out1;
+  int32_t ld_in0, ld_in1, ld_in2, ld_out0, ld_out1;
+  int32_t ncols, aux;
+} hold_ew_args;
+int hold_train_ew(hold_ctx* ctx, int op, int P, const hold_ew_args* args, void* stream);
 /* KNNDeformer.forward(inverse=True) / ObjectDeformer.forward(inverse=True): x [B,P,3] -> x_c, knn idx [B,P,15] (opt). */
 int hold_inverse_warp(hold_ctx* ctx, int node, int B, int P, const float* x, const hold_node_pose* pose,
                       float* x_c, int32_t* knn_idx, uint8_t* outlier_mask, void* stream);

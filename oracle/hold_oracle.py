@@ -541,6 +541,51 @@ def node_forward(kind, class_id, dirs, cam, frame_of_ray, sdf_sd, rgb_sd, beta_p
     }
 
 
+def node_forward_train(kind, x, frame_of_point, sdf_sd, rgb_sd, beta_param, tfs, posed_verts=None, cano_verts=None, skin_W=None,
+                       pose_cond=None, time_code=None, embed_w=None):
+    """Node.forward after sampling in TRAINING mode (node.py:57-87; extract_features with create_graph=True,
+    volsdf_utils.py:51-147): deformed points x [P,3] (frames given by frame_of_point) -> dict(sdf, x_c, feat, grad, normal, color,
+    density) with the autograd graph attached to every tensor among (state dicts, beta_param, tfs, pose_cond, time_code) that
+    requires grad.  Skinning weights are detached (mano/deformer.py:101)."""
+    xc = torch.empty_like(x)
+    Jl = torch.empty(x.shape[0], 3, 3, dtype=x.dtype)
+    parts = []
+    order = []
+    for b in frame_of_point.unique().tolist():
+        m = (frame_of_point == b).nonzero()[:, 0]
+        if kind == "hand":
+            w, _, _ = skin_weights_query(x[m].detach(), posed_verts[b].detach(), skin_W)
+            Tm = torch.einsum("pn,nij->pij", w.detach(), tfs[b])
+            xh = F.pad(x[m], (0, 1), value=1.0)
+            parts.append(torch.einsum("pij,pj->pi", Tm.inverse(), xh)[:, :3])
+        else:
+            xh = F.pad(x[m], (0, 1), value=1.0)
+            parts.append((xh @ tfs[b].inverse().T)[:, :3])
+        order.append(m)
+    perm = torch.cat(order)
+    x_c = torch.empty_like(x).index_copy(0, perm, torch.cat(parts))
+    cond = torch.zeros(x.shape[0], 45, dtype=x.dtype) if kind == "hand" else None
+    xg = x_c if x_c.requires_grad else x_c.clone().requires_grad_(True)
+    out = sdf_mlp(xg, sdf_sd, cond, embed_w)
+    sdf, feat = out[:, 0], out[:, 1:]
+    g = torch.autograd.grad(sdf.sum(), xg, create_graph=True)[0]
+    Js = []
+    for b in frame_of_point.unique().tolist():
+        m = (frame_of_point == b).nonzero()[:, 0]
+        if kind == "hand":
+            w, _, _ = skin_weights_query(x_c[m].detach(), cano_verts, skin_W)
+            Js.append(torch.einsum("pn,nij->pij", w.detach(), tfs[b])[:, :3, :3])
+        else:
+            Js.append(tfs[b][:3, :3][None].expand(m.shape[0], 3, 3))
+    J = torch.empty(x.shape[0], 3, 3, dtype=x.dtype).index_copy(0, perm, torch.cat(Js))
+    normal = F.normalize(torch.einsum("bi,bij->bj", g, J.inverse()), dim=1, eps=1e-6)
+    f2 = feat if time_code is None else torch.cat([feat, time_code[frame_of_point]], -1)
+    pc = None if pose_cond is None else pose_cond[frame_of_point]
+    color = rgb_mlp(x_c, normal, pc, f2, rgb_sd)
+    density = laplace_density(sdf, density_beta(beta_param))
+    return dict(sdf=sdf, x_c=x_c, feat=feat, grad=g, normal=normal, color=color, density=density)
+
+
 def composite(factors_list, stable=False):
     """HOLDNet.forward_fg, hold/hold_net.py:76-88: composite render + per-node renders."""
     comp = merge_factors(factors_list, stable)

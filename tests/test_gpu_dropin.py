@@ -37,13 +37,14 @@ def test_sampler_with_the_reference_call(env, ctx):
         node, a = env["net"].nodes[nid], env["art"][nid]
         smp = dropin.ErrorBoundSampler(sc.bounding_sphere, inverse_sphere_bg=True, **{k: v for k, v in sc.sampler.items()})
         deformer = dropin.MANODeformer(node) if nid != "object" else dropin.ObjectDeformer(node)
+        # the servers' own outputs (what mano_node.py:72-98 / object_node.py:58-82 put into deform_info)
+        pose, keep, srv, tfs = node.articulate(env["inp"])
         if nid != "object":
-            deform_info = {"cond": {"pose": a["pose_cond"].to(dev)}, "tfs": a["tfs"].to(dev), "verts": a["verts"].to(dev)}
+            deform_info = {"cond": {"pose": a["pose_cond"].to(dev)}, "tfs": srv["tfs"], "verts": srv["verts"]}
         else:
-            deform_info = {"cond": {"pose": torch.zeros(sc.B, 0, device=dev)}, "tfs": a["tfs"].to(dev)}
+            deform_info = {"cond": {"pose": torch.zeros(sc.B, 0, device=dev)}, "tfs": srv["obj_tfs"]}
         z = smp.get_z_vals(dropin.sdf_func_with_deformer, deformer, node.implicit_network, dirs, cam, node.density, False, deform_info)
         ctx.check()
-        pose, keep, _, _ = node.articulate(env["inp"])
         z2, it2 = Mirror(node).get_z_vals(dirs, cam, pose, sc.B)
         assert torch.equal(z, z2), f"{nid}: adaptor and mirror run the same kernels on the same inputs"
         assert int(smp.last_iters.item()) == int(it2.item())

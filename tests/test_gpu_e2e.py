@@ -18,6 +18,7 @@ def e2e_close(a, b, name, tol=1e-4, tol_max=1e-2, frac_min=0.97):
     scale = max(1.0, b.abs().max().item())
     d = (a - b).abs()
     frac = (d <= tol * scale).float().mean().item()
+    print(f"  e2e {name}: within {tol:.0e}: {frac:.4f}, max {d.max().item() / scale:.2e} of scale")
     assert frac >= frac_min, f"{name}: only {frac:.4f} within {tol} (max {d.max().item():.3e})"
     assert d.max().item() <= tol_max * scale, f"{name}: max|d| {d.max().item():.3e}"
 
@@ -43,11 +44,11 @@ def test_golden(path, mode, ctx):
         if nid != "object":
             e2e_close(art["tfs"], rec["art"][nid]["tfs"], f"{nid}.tfs", 1e-5, 1e-4)
             e2e_close(art["jnts"], rec["art"][nid]["jnts"], f"{nid}.jnts", 1e-5, 1e-4)
-        # HOLD_MLP_FP32 (exact fp32 arithmetic): >= 97 % of the pixels within 1e-4.  HOLD_MLP_TC: the tensor core's
-        # fp32 accumulator is truncated on each of the 48 MMA accumulations of a layer, which leaves a 6e-6 relative
-        # error on the sdf (measured, independent of the operand split: bf16 1.2e-5, fp16 5.9e-6); the Laplace
-        # density amplifies an sdf error by 1/beta^2, so at beta = 0.03 ~14 % of the pixels move by 1e-4..4e-3.
-        fmin, emax = (0.97, 1e-2) if mode == "fp32" else (0.80, 3e-2)
+        # Both arithmetic modes are held to the same bar (round 2: accumulator-truncation compensation brought the tensor-core
+        # sdf to fp32 level, profiles/r02_tc_accumulator_bias.md): >= 95 % of the pixels within 1e-4 and max <= 1e-2, i.e. <= 3x
+        # the worst values measured over the three goldens (fp32: 97.9 % / 3.0e-3; tensor cores: 96.1 % / 3.4e-3).  The residual is
+        # the sampler's sensitivity to the last bit of exp() (tests/test_gpu_sampler_rounds.py quantifies it round by round).
+        fmin, emax = 0.95, 1e-2
         for k in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
             e2e_close(out[f"{nid}.{k}"], rec["render"][nid][k], f"{nid}.{k}", tol_max=emax, frac_min=fmin)
     # Composite: the reference sorts the concatenated z of all nodes with an UNSTABLE torch.sort; exact z ties
@@ -68,7 +69,16 @@ def test_golden(path, mode, ctx):
     # 1e-2 (rgb) / 3.7e-2 (depth) with 76-95 % of the pixels beyond 1e-4 while its per-node renders stay within
     # 1.3e-4 — the interleaving of the nodes' sample sets amplifies sample-position noise.  The composite is
     # therefore held to a mean/max bound here; its 1e-5 stage parity (same factors in) is test_gpu_stages.py.
+    # Bounds per golden = <= 3x the values measured on hardware in round 2 (worst of both modes and of the six quantities):
+    #   c1 64x64 S=32 n=2: mean 3.0e-5, max 1.5e-2, 98.96 % within 1e-4;  S=128 n=2 beta 0.03: 1.15e-3 / 4.9e-2 / 77 %;
+    #   S=128 n=3 beta 0.05: 1.34e-3 / 5.8e-2 / 66 %.
+    name = os.path.basename(path)[:-3]
+    mean_max, abs_max, frac_min = {"c1_64x64_S32_n2": (1e-4, 4.5e-2, 0.97), "s128_n2_beta03": (3.5e-3, 1.5e-1, 0.60),
+                                   "s128_n3_beta05": (4e-3, 1.7e-1, 0.50)}.get(name, (4e-3, 1.7e-1, 0.50))
     for k in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
         a, b = out[k].detach().float().cpu().reshape(canon[k].shape), canon[k]
         d = (a - b).abs()
-        assert d.mean().item() <= 8e-3 and d.max().item() <= 1.5e-1, f"comp.{k}: mean {d.mean().item():.2e} max {d.max().item():.2e}"
+        frac = (d <= 1e-4 * max(1.0, b.abs().max().item())).float().mean().item()
+        print(f"  e2e comp.{k}: mean {d.mean().item():.2e} max {d.max().item():.2e} within 1e-4: {frac:.4f}")
+        assert d.mean().item() <= mean_max and d.max().item() <= abs_max and frac >= frac_min, \
+            f"comp.{k}: mean {d.mean().item():.2e} max {d.max().item():.2e} within-1e-4 {frac:.3f}"

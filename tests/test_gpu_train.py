@@ -1,0 +1,165 @@
+"""SURVEY §8f rank 2 — the training backward on the GPU (hold_b200/train.py: autograd Functions over hold_linear /
+hold_train_ew / the warp and server backward kernels) against torch.autograd over the oracle in float64 on the CPU
+(the reference differentiates with autograd, incl. the double backward through the normals, volsdf_utils.py:123-131).
+Gradients are compared relative to the largest entry of each gradient tensor: 1e-4 (north-star bar)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, r):
+    a, r = a.detach().double().cpu(), r.detach().double().cpu()
+    return ((a - r).abs().max() / r.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def env(ctx):
+    from hold_b200 import capi, scene_io, synth
+    from oracle import hold_oracle as O
+
+    sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), B=2, seed=6, perturb=0.02)
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    return dict(sc=sc, net=net, dev=torch.device("cuda", 0), O=O, art=O.scene_articulation(sc))
+
+
+def _params64(sd):
+    return {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("nid", ["right", "object"])
+def test_sdf_net_function(env, ctx, nid):
+    from hold_b200 import train
+
+    sc, O, dev = env["sc"], env["O"], env["dev"]
+    node = env["net"].nodes[nid]
+    g = torch.Generator().manual_seed(3)
+    P = 2500
+    x = ((torch.rand(P, 3, generator=g) - 0.5) * 1.6)
+    d_sdf, d_feat, d_g = torch.randn(P, generator=g), torch.randn(P, 256, generator=g) * 0.1, torch.randn(P, 3, generator=g)
+    # ---- reference: autograd in float64
+    sd = _params64(sc.sdf_state[nid])
+    xr = x.double().requires_grad_(True)
+    out = O.sdf_mlp(xr, sd, torch.zeros(P, 45, dtype=torch.float64) if nid != "object" else None)
+    gr = torch.autograd.grad(out[:, 0].sum(), xr, create_graph=True)[0]
+    loss = (out[:, 0] * d_sdf.double()).sum() + (out[:, 1:] * d_feat.double()).sum() + (gr * d_g.double()).sum()
+    loss.backward()
+    # ---- GPU
+    node.sync_weights()
+    for p in node.implicit_network.parameters():
+        p.grad = None
+    xg = x.to(dev).requires_grad_(True)
+    Ws, bs = train._folded_sdf(node)
+    sdf, feat, gg = train.SdfNetFn.apply(node, xg, *Ws, *bs)
+    ctx.check()
+    assert rel(sdf, out[:, 0]) < TOL and rel(feat, out[:, 1:]) < TOL and rel(gg, gr) < TOL
+    l2 = (sdf * d_sdf.to(dev)).sum() + (feat * d_feat.to(dev)).sum() + (gg * d_g.to(dev)).sum()
+    l2.backward()
+    ctx.check()
+    worst = rel(xg.grad, xr.grad)
+    print(f"{nid}: d_x {worst:.2e}")
+    assert worst < TOL
+    for l in range(9):
+        lin = getattr(node.implicit_network, f"lin{l}")
+        for name, t in (("weight_v", lin.weight_v), ("weight_g", lin.weight_g), ("bias", lin.bias)):
+            e = rel(t.grad, sd[f"lin{l}.{name}"].grad)
+            print(f"{nid}: lin{l}.{name} {e:.2e}")
+            assert e < TOL, f"{nid} lin{l}.{name}: {e:.2e}"
+
+
+@pytest.mark.parametrize("nid", ["right", "object"])
+def test_rgb_net_function(env, ctx, nid):
+    from hold_b200 import train
+
+    sc, O, dev = env["sc"], env["O"], env["dev"]
+    node = env["net"].nodes[nid]
+    g = torch.Generator().manual_seed(4)
+    P = 2000
+    K0 = 270 if nid != "object" else 302
+    inp = torch.randn(P, K0, generator=g) * 0.4
+    d_rgb = torch.randn(P, 3, generator=g)
+    sd = _params64(sc.rgb_state[nid])
+    ir = inp.double().requires_grad_(True)
+    h = ir
+    for l in range(5):
+        h = torch.nn.functional.linear(h, O.wn(sd, f"lin{l}"), sd[f"lin{l}.bias"])
+        if l < 4:
+            h = torch.relu(h)
+    ref = torch.sigmoid(h)
+    (ref * d_rgb.double()).sum().backward()
+    node.sync_weights()
+    for p in node.rendering_network.parameters():
+        p.grad = None
+    ig = inp.to(dev).requires_grad_(True)
+    Wr, br = train._folded_rgb(node)
+    rgb = train.RgbNetFn.apply(node, ig, *Wr, *br)
+    ctx.check()
+    assert rel(rgb, ref) < TOL
+    (rgb * d_rgb.to(dev)).sum().backward()
+    ctx.check()
+    assert rel(ig.grad, ir.grad) < TOL, rel(ig.grad, ir.grad)
+    for l in range(5):
+        lin = getattr(node.rendering_network, f"lin{l}")
+        for name, t in (("weight_v", lin.weight_v), ("weight_g", lin.weight_g), ("bias", lin.bias)):
+            e = rel(t.grad, sd[f"lin{l}.{name}"].grad)
+            assert e < TOL, f"{nid} rgb lin{l}.{name}: {e:.2e}"
+
+
+@pytest.mark.parametrize("nid", ["right", "object"])
+def test_node_training_forward_backward(env, ctx, nid):
+    """Node.forward after sampling, training mode: every output and the gradients of a random linear functional of (color,
+    density, normal) w.r.t. both nets' parameters, beta, the bone / object transforms and the frame / pose codes."""
+    from hold_b200 import train
+
+    sc, O, dev, a = env["sc"], env["O"], env["dev"], env["art"][nid]
+    node = env["net"].nodes[nid]
+    hand = nid != "object"
+    g = torch.Generator().manual_seed(5)
+    B, P = sc.B, 600
+    x = (torch.rand(B, P, 3, generator=g) - 0.5) * 1.2
+    fr = torch.arange(B).repeat_interleave(P)
+    cw, dw, nw = torch.randn(B * P, 3, generator=g), torch.randn(B * P, generator=g) * 0.01, torch.randn(B * P, 3, generator=g) * 0.1
+    # ---- reference (float64 autograd)
+    sds, sdr = _params64(sc.sdf_state[nid]), _params64(sc.rgb_state[nid])
+    beta = sc.beta[nid].double().clone().requires_grad_(True)
+    tfs = a["tfs"].double().clone().requires_grad_(True)
+    pc = a["pose_cond"].double().clone().requires_grad_(True) if hand else None
+    tc = sc.time_code.double().clone().requires_grad_(True) if not hand else None
+    r = O.node_forward_train(a["kind"], x.reshape(-1, 3).double(), fr, sds, sdr, beta, tfs, posed_verts=a.get("verts").double() if hand else None,
+                             cano_verts=a.get("cano_verts").double() if hand else None, skin_W=a.get("skin_W").double() if hand else None,
+                             pose_cond=pc, time_code=tc)
+    (r["color"] * cw.double()).sum().add((r["density"] * dw.double()).sum()).add((r["normal"] * nw.double()).sum()).backward()
+    # ---- GPU
+    for p in node.parameters():
+        p.grad = None
+    tg = a["tfs"].to(dev).requires_grad_(True)
+    pg = a["pose_cond"].to(dev).requires_grad_(True) if hand else None
+    cg = sc.time_code.to(dev).clone().requires_grad_(True) if not hand else None
+    o = train.node_forward_train(node, x.to(dev), tg, a["verts"].to(dev) if hand else None, fr.to(dev), pose_cond=pg, time_code=cg)
+    ctx.check()
+    for k in ("sdf", "x_c", "feat", "grad", "normal", "color", "density"):
+        e = rel(o[k], r[k])
+        print(f"{nid}: forward {k} {e:.2e}")
+        assert e < (2e-4 if k == "normal" else TOL), f"{nid} {k}: {e:.2e}"
+    ((o["color"] * cw.to(dev)).sum() + (o["density"] * dw.to(dev)).sum() + (o["normal"] * nw.to(dev)).sum()).backward()
+    ctx.check()
+    # transforms: the three affine rows.  The bottom row of every bone / object transform is the constant [0, 0, 0, s] produced by
+    # the servers (no parameter reaches it), so the kernels do not differentiate with respect to it (hold_inverse_warp_bwd).
+    checks = [("tfs[..., :3, :]", tg.grad[..., :3, :], tfs.grad[..., :3, :]), ("beta", node.density.beta.grad, beta.grad)]
+    if hand:
+        checks.append(("pose_cond", pg.grad, pc.grad))
+    else:
+        checks.append(("time_code", cg.grad, tc.grad))
+    for l in range(9):
+        lin = getattr(node.implicit_network, f"lin{l}")
+        checks += [(f"sdf.lin{l}.weight_v", lin.weight_v.grad, sds[f"lin{l}.weight_v"].grad), (f"sdf.lin{l}.bias", lin.bias.grad, sds[f"lin{l}.bias"].grad)]
+    for l in range(5):
+        lin = getattr(node.rendering_network, f"lin{l}")
+        checks += [(f"rgb.lin{l}.weight_v", lin.weight_v.grad, sdr[f"lin{l}.weight_v"].grad)]
+    if hand:
+        checks.append(("rgb.lin_pose.weight", node.rendering_network.lin_pose.weight.grad, sdr["lin_pose.weight"].grad))
+    for name, got, want in checks:
+        e = rel(got, want)
+        print(f"{nid}: grad {name} {e:.2e}")
+        assert e < 3e-4, f"{nid} grad {name}: {e:.2e}"
