@@ -422,6 +422,42 @@ def main():
         "whole_step_frac_of_sustained": world * flops_per_ray(max(iters)) * R * args.steps / (ms * 1e-3) / 1e12 / (sustained * world),
     }
 
+    # ---- extra fields (same JSON line): the full HOLDNet.forward with the NeRF++ background leg on this workload, and
+    # BASELINE configs[2] (two hands + object, 289 merged samples).  1 warm-up + 2 timed frames each, this rank only.
+    extras = None
+    if not args.no_extras and use_tc:
+        from hold_b200.model import HOLDNet
+
+        extras = {}
+        bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=mode)
+        full = HOLDNet(ctx, dict(net.nodes), background=bg)
+        full(inp_dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            full(inp_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        extras["full_forward_with_background_rays_per_s"] = world * R * 2 / (e0.elapsed_time(e1) * 1e-3)
+        from hold_b200 import synth
+
+        sc3 = synth.make_scene(H=H, W=W, S=S, nodes=("right", "left", "object"), B=1, seed=0)
+        for nid in sc3.node_ids:
+            sc3.beta[nid] = torch.tensor(BETA)
+        net3 = scene_io.build_net(sc3, ctx, mode)
+        inp3 = scene_io.scene_input(sc3, dev)
+        o3 = net3.forward_fg(inp3, return_factors=False, want_weights=False)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(2):
+            o3 = net3.forward_fg(inp3, return_factors=False, want_weights=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ctx.check()
+        extras["configs[2]_two_hands_object_rays_per_s"] = world * R * 2 / (e0.elapsed_time(e1) * 1e-3)
+        extras["configs[2]_sampler_rounds"] = [int(x) for x in o3["sampler_iters"].tolist()]
+        extras["note"] = "per-rank measurements x world; same 512x512 frame, beta 0.03; background nets on tcgen05"
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -443,6 +479,8 @@ def main():
         "clocks": clocks.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "extras": extras,
+        "env": {k: v for k, v in os.environ.items() if k.startswith("HOLD_")},   # the library reads no environment; these steer bench.py only
     }
     print(json.dumps(line))
     if dist is not None:
