@@ -79,6 +79,17 @@ def _gloo_worker(rank, world, port, q):
     g1, g2 = torch.full((10,), float(rank + 1)), torch.full((2, 3), 10.0 * (rank + 1))
     allreduce_flat_([g1, None, g2])
     ok_ar = bool((g1 == 3.0).all() and (g2 == 30.0).all())
+    # gradient buckets keep the same layout on every rank even when a rank has no gradient for a parameter (a node none of its
+    # rays hit): rank 0 lacks p2's gradient, rank 1 lacks p1's
+    from hold_b200.shard import allreduce_grads_
+    p1, p2, p3 = (torch.nn.Parameter(torch.zeros(5)) for _ in range(3))
+    if rank == 0:
+        p1.grad = torch.full((5,), 2.0)
+    else:
+        p2.grad = torch.full((5,), 7.0)
+    p3.grad = torch.full((5,), float(rank + 1))
+    allreduce_grads_([p1, p2, p3], average=True)
+    ok_ar = ok_ar and bool((p1.grad == 1.0).all() and (p2.grad == 3.5).all() and (p3.grad == 1.5).all())
     # image assembly on rank 0
     local = torch.arange(s, e, dtype=torch.float32)[:, None].repeat(1, 3)
     full = gather_rays(local, n, rank, world)
