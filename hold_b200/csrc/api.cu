@@ -134,9 +134,13 @@ static int launch_inverse_warp(hold_ctx* ctx, NodeState& ns, int B, int pts_per_
   }
   if (hand && from_z && knn_idx == nullptr && outlier == nullptr) {
     // hot path: consecutive samples of a ray per thread, KNN seeded from the previous sample
-    const int rays = pts_per_frame / nsamp, segs = ceil_div(nsamp, kSeg);
+    const int rays = pts_per_frame / nsamp;
+    // walk length per thread: 32 samples when that still fills the GPU (>= 2 waves of 4 blocks per SM), else shorter walks
+    int seg_len = kSeg;
+    while (seg_len > 4 && (long long)B * rays * ceil_div(nsamp, seg_len) < (long long)ctx->sm_count * 4 * 128 * 2) seg_len >>= 1;
+    const int segs = ceil_div(nsamp, seg_len);
     dim3 g2(ceil_div(rays * segs, 128), B);
-    k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, ns.knn_perm, xc, st);
+    k_inverse_warp_hand_rays<<<g2, 128, 0, s>>>(rays, nsamp, seg_len, zstride, zbuf, cam, dirs, pose->tfs, pose->posed_verts, ns.skin_w, ns.knn_perm, xc, st);
     HOLD_LAUNCH_CHECK(ctx);
     return HOLD_OK;
   }
@@ -896,6 +900,7 @@ int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
 int hold_debug_set(hold_ctx* ctx, int key, int value) {
   if (!ctx) return HOLD_E_BADARG;
   if (key == 2) ctx->tc_acc_comp = value;
+  else if (key == 3) ctx->sampler_passes = value;
   else return HOLD_E_BADARG;
   return HOLD_OK;
 }

@@ -72,7 +72,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   }
   a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last;
   a.cam = cam, a.dirs = dirs, a.frame_code = frame_code, a.r_sphere = r_sphere;
-  a.sdf = sdf, a.feat = feat, a.err = ctx->dev_err, a.unscale = kTcUnscale;
+  a.sdf = sdf, a.feat = feat, a.err = ctx->dev_err, a.unscale = kTcUnscale, a.passes = 3;
   const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
   k_mlp_tc<MLP_BG_SDF><<<grid, kTcThreadsTotal, TcCfg<MLP_BG_SDF>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
@@ -81,7 +81,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   c.P = P, c.n_layers = 1, c.pts_per_frame = P;
   c.L[0].wimg = t.rgb_img, c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].nst = 10, c.L[0].N = 256;
   c.w_last = t.rgb_w_last, c.b_last = ctx->bg_rgb.b_last;
-  c.dirs = dirs, c.frame_code = frame_code, c.feat = feat, c.rgb = rgb, c.err = ctx->dev_err, c.unscale = kTcUnscale;
+  c.dirs = dirs, c.frame_code = frame_code, c.feat = feat, c.rgb = rgb, c.err = ctx->dev_err, c.unscale = kTcUnscale, c.passes = 3;
   c.k0 = kBgView + kBgFrame + kFeat;
   k_mlp_tc<MLP_BG_RGB><<<grid, kTcThreadsTotal, TcCfg<MLP_BG_RGB>::kSmemBytes, s>>>(c);
   HOLD_LAUNCH_CHECK(ctx);

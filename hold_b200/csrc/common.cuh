@@ -75,6 +75,7 @@ struct hold_ctx {
   bool has_bg = false;
   int bg_mlp_mode = 0;             // HOLD_MLP_* of the background nets (hold_bg_set_weights)
   hold::TcBg* bg_tc = nullptr;
+  int sampler_passes = 3;          // measurement hook (hold_debug_set key 3): MMA passes of the sampler-round SDF launches
   int tc_acc_comp = -1;            // measurement hook (hold_debug_set key 2): accumulator scale 1 + c * 2^-24 in the SDF chains; < 0: kTcAccComp
 };
 

@@ -202,9 +202,9 @@ k_inverse_warp(int pts_per_frame, int ns, int zstride, const float* __restrict__
 // samples of one ray and finds each sample's 15 nearest posed vertices with the seeded, cluster-pruned exact search of
 // knn_phases.h (same neighbours, same order as the full scan of knn15).  A warp holds 32 CONSECUTIVE rays at the same depth
 // segment, so its lanes prune nearly the same vertex groups.  Same arithmetic downstream, same results.
-constexpr int kSeg = 32;
+constexpr int kSeg = 32;   // samples per thread at frame-sized launches; small launches (a training batch) use shorter walks
 __global__ void __launch_bounds__(128)
-k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* __restrict__ zbuf,
+k_inverse_warp_hand_rays(int rays_per_frame, int ns, int seg_len, int zstride, const float* __restrict__ zbuf,
                          const float* __restrict__ cam, const float* __restrict__ dirs, const float* __restrict__ tfs,
                          const float* __restrict__ verts, const float* __restrict__ skin_w, const unsigned short* __restrict__ perm,
                          float* __restrict__ xc, const SamplerState* __restrict__ st) {
@@ -228,7 +228,7 @@ k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* _
   __syncthreads();
   if (threadIdx.x < knnc::kNCl) scl[threadIdx.x] = knnc::make_cluster(svc + threadIdx.x * knnc::kClSize);
   __syncthreads();
-  const int segs = (ns + kSeg - 1) / kSeg;
+  const int segs = (ns + seg_len - 1) / seg_len;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rays_per_frame * segs) return;
   const int seg = t / rays_per_frame, ray_in_frame = t - seg * rays_per_frame;
@@ -236,7 +236,7 @@ k_inverse_warp_hand_rays(int rays_per_frame, int ns, int zstride, const float* _
   const float cx = cam[3 * ray], cy = cam[3 * ray + 1], cz = cam[3 * ray + 2];
   const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
   knnc::Top top;
-  const int k0 = seg * kSeg, k1 = min(ns, k0 + kSeg);
+  const int k0 = seg * seg_len, k1 = min(ns, k0 + seg_len);
   for (int k = k0; k < k1; ++k) {
     const float tz = zbuf[ray * zstride + k];
     const float x = __fadd_rn(cx, __fmul_rn(tz, dx)), y = __fadd_rn(cy, __fmul_rn(tz, dy)), z = __fadd_rn(cz, __fmul_rn(tz, dz));

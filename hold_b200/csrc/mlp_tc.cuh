@@ -93,6 +93,8 @@ struct TcArgs {
   const float* in_scale;     // device scalar s (a power of two) or NULL: A is fed as A / s, C comes out times s (keeps tiny gradients
                              // inside the fp16 hi/lo split's range)
   int lda, ldc, kvalid, nvalid;
+  int passes;                // MMAs per product: 3 = hi*hi + lo*hi + hi*lo (always, in production); 2 / 1 only through the measurement
+                             // hook hold_debug_set(ctx, 3, n) for the sampler rounds (profiles/r02_sampler_precision.md)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
               if (el) {
                 tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
-                tc_mma(d_tmem, alo, whi, kIdescF16, 1);
-                tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
+                if (a.passes >= 2) tc_mma(d_tmem, alo, whi, kIdescF16, 1);
+                if (a.passes >= 3) tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
               }
             }
             if (el) tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
@@ -989,6 +991,7 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
+  a.passes = (st != nullptr && ctx->sampler_passes >= 1 && ctx->sampler_passes <= 3) ? ctx->sampler_passes : 3;
   a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));
   const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
   if (rev) {
@@ -1026,6 +1029,7 @@ static int tc_launch_linear(hold_ctx* ctx, NodeState& ns, int mat, int P, const 
   HOLD_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Cout & 15) == 0, "hold_linear: rows must be 16-byte aligned");
   HOLD_REQUIRE(!add_bias || bias != nullptr, "hold_linear(%d): this matrix has no bias", mat);
   a.L[0].wimg = img, a.L[0].bias = add_bias ? bias : nullptr, a.L[0].nst = nst, a.L[0].N = nvalid;
+  a.passes = 3;
   a.lin_in = A, a.lda = lda, a.kvalid = kvalid, a.lin_out = Cout, a.ldc = ldc, a.nvalid = nvalid, a.in_scale = in_scale;
   a.err = ctx->dev_err, a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));
   const int tiles = ceil_div(P, kTcRows);
@@ -1044,7 +1048,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   }
   a.w_last = ns.rgb.w_last, a.b_last = ns.rgb.b_last;
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
-  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err, a.unscale = kTcUnscale;
+  a.pts_per_frame = pts_per_frame, a.k0 = ns.rgb.K[0], a.rgb = rgb, a.err = ctx->dev_err, a.unscale = kTcUnscale, a.passes = 3;
   int tiles = ceil_div(P, kTcRows);
   k_mlp_tc<MLP_COLOR><<<min(tiles, ctx->sm_count), kTcThreadsTotal, TcCfg<MLP_COLOR>::kSmemBytes, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);

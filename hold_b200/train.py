@@ -297,15 +297,17 @@ def node_forward_train(node, x, tfs, verts, frame_of_point, pose_cond=None, time
         d2 = ((x_c.detach().reshape(B * P, 1, 3) - cano[idx.reshape(B * P, 15).long()]) ** 2).sum(-1).clamp(max=4.0)
         conf = torch.softmax(-d2, dim=1)
         w = (node.server.m["lbs_weights"][idx.reshape(B * P, 15).long()] * conf[..., None]).sum(1)         # [BP,16], detached by construction
-        J = torch.einsum("pn,pnij->pij", w, tfs[frame_of_point][:, :, :3, :3])
+        # points are frame-major (B blocks of P): one batched [P,16] x [16,9] product per frame instead of a per-point gather of
+        # the 16 bone transforms (whose backward is a slow scatter-add)
+        J = torch.bmm(w.reshape(B, P, 16), tfs[:, :, :3, :3].reshape(B, 16, 9)).reshape(B * P, 3, 3)
     else:
-        J = tfs.reshape(B, 4, 4)[frame_of_point][:, :3, :3]
+        J = tfs.reshape(B, 1, 4, 4)[:, :, :3, :3].expand(B, P, 3, 3).reshape(B * P, 3, 3)
     normal = torch.nn.functional.normalize(torch.einsum("bi,bij->bj", g, torch.linalg.inv(J)), dim=1, eps=1e-6)
     if node.kind == "hand":
-        pe = node.rendering_network.lin_pose(pose_cond)[frame_of_point]
+        pe = node.rendering_network.lin_pose(pose_cond)[:, None, :].expand(B, P, 8).reshape(B * P, 8)   # per-frame rows, frame-major points
         inp = torch.cat([x_c, normal, pe, feat], 1)
     else:
-        inp = torch.cat([x_c, normal, x_c.new_zeros(B * P, 8), feat, time_code[frame_of_point]], 1)
+        inp = torch.cat([x_c, normal, x_c.new_zeros(B * P, 8), feat, time_code[:, None, :].expand(B, P, 32).reshape(B * P, 32)], 1)
     Wr, br = _folded_rgb(node)
     color = RgbNetFn.apply(node, inp, *Wr, *br)
     density = laplace_density(sdf, node.density.get_beta())

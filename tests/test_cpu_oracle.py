@@ -1,5 +1,5 @@
 """CPU-only: the oracle (oracle/hold_oracle.py) against the committed golden fixtures, which were produced by the
-REFERENCE's own modules (oracle/ref_harness.py golden).  Same criteria as ref_harness.check()."""
+REFERENCE's own modules (oracle/ref_harness.py golden)."""
 import glob
 import os
 
@@ -39,16 +39,18 @@ def test_oracle_matches_reference_golden(path):
         assert _close(art[nid]["verts"], rec["art"][nid]["verts"], 1e-6, 1e-5)
         n, g = outs[0]["nodes"][k], rec["nodes"][nid]
         w = outs[0]["render"][k]["fg_weights"]
+        # Bounds = <= 3x what this comparison measures (oracle here vs goldens written by the reference modules in another process:
+        # same algorithm, same libm, different GEMM blocking).  Measured worst case over the three goldens: per-sample tensors
+        # 97.4 % within 1e-4 (normals, weight-carrying max 8.3e-2; others <= 5.7e-3); per-node renders 95.05 % / max 3.1e-3;
+        # composite mean 4.0e-4, max 2.7e-2.  That the SAME algorithm moves this much between two processes is the reference's own
+        # sensitivity (tests/test_gpu_sampler_rounds.py); the tight same-process pin is tests/test_cpu_oracle_pin.py.
         for key in ("z_vals", "sdf", "canonical_pts", "normal", "color"):
-            # per-sample tensors inherit the sampler's position noise (flat-PDF regions, tools/noise_floor.py)
-            assert _close(n[key], g[key], w=w, tol_max=1e-1, frac_min=0.9), f"{nid}.{key}"
+            assert _close(n[key], g[key], w=w, tol_max=(1e-1 if key == "normal" else 1.5e-2), frac_min=0.97), f"{nid}.{key}"
         for key in ("fg_rgb", "mask_prob", "depth", "normal", "bg_weights"):
-            # (the golden file was written by the reference modules in another process: BLAS blocking differs by
-            #  batch shape, and at beta = 0.03 that alone moves ~5 % of the hand's pixels by up to 3e-3)
-            assert _close(outs[0]["render"][k][key], rec["render"][nid][key], tol_max=1e-2, frac_min=0.9), f"{nid}.render.{key}"
+            assert _close(outs[0]["render"][k][key], rec["render"][nid][key], tol_max=1e-2, frac_min=0.94), f"{nid}.render.{key}"
     for key in ("fg_rgb", "mask_prob", "depth", "normal", "fg_semantics", "bg_weights"):
         d = (outs[0]["render"]["comp"][key] - rec["render"]["comp"][key]).abs()
-        assert d.mean().item() <= 3e-3 and d.max().item() <= 6e-2, f"comp.{key}"
+        assert d.mean().item() <= 1.2e-3 and d.max().item() <= 8e-2, f"comp.{key}"
 
 
 def test_oracle_edge_cases():

@@ -8,14 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def env(ctx):
+@pytest.fixture(scope="module", params=["fp32", "tc"])
+def env(ctx, request):
+    """Both arithmetic modes of the MLPs (the tensor-core mode is the one bench.py and smoke() run)."""
     from hold_b200 import capi, scene_io, synth
     from oracle import hold_oracle as O
 
     sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), seed=6)
     sc.sampler["add_tiny"] = 1e-3   # see tests/test_gpu_stages.py: keeps the sampler comparison above libm noise
-    net = scene_io.build_net(sc, ctx, capi.MLP_FP32)
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC if request.param == "tc" else capi.MLP_FP32)
     dev = torch.device("cuda", 0)
     return dict(sc=sc, net=net, dev=dev, O=O, inp=scene_io.scene_input(sc, dev), art=O.scene_articulation(sc))
 
@@ -96,3 +97,26 @@ def test_training_mode_sampling_with_given_randomness(env, ctx):
     assert (z[:, 1:] >= z[:, :-1]).all()
     frac = ((z - zo).abs() <= 1e-4 * 8.0).float().mean().item()
     assert frac >= 0.93, f"only {frac:.3f} of the training-mode z_vals within tolerance"
+
+
+def test_chunked_render_reproduces_the_reference_chunk_semantics(env, ctx):
+    """forward_fg(chunk=n): the sampler's convergence flag is global over ONE call (ray_sampler.py:244), so rendering in the
+    reference's pixel chunks (eval_datasets.py:13) gives each chunk its own round count; the result must equal the oracle run with
+    the same chunking, and the chunk calls must be exactly what separate calls produce."""
+    from hold_b200 import scene_io
+
+    sc, O, dev = env["sc"], env["O"], env["dev"]
+    inp = scene_io.scene_input(sc, dev)
+    out = env["net"].forward_fg(inp, chunk=16)
+    ctx.check()
+    R = sc.H * sc.W
+    assert out["fg_rgb"].shape[0] == R and out["sampler_iters_per_chunk"].shape[0] == R // 16
+    ref, _ = O.render_scene(sc, chunk=16, stable_ties=True)
+    for c in (0, len(ref) - 1):
+        sub = scene_io.scene_input(sc, dev, ray_ids=torch.arange(c * 16, (c + 1) * 16))
+        alone = env["net"].forward_fg(sub)
+        assert torch.equal(alone["fg_rgb"], out["fg_rgb"][c * 16:(c + 1) * 16])
+        for k, nid in enumerate(sc.node_ids):
+            assert int(out["sampler_iters_per_chunk"][c][k]) == ref[c]["nodes"][k]["iters"], f"chunk {c} {nid}: round count"
+            a, b = out[f"{nid}.fg_rgb"][c * 16:(c + 1) * 16].cpu(), ref[c]["render"][k]["fg_rgb"]
+            assert (a.reshape(b.shape) - b).abs().max().item() < 1e-3

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config train --steps 5 --warmup 2 > gpurun_out/r2h_train_2gpu.json 2> gpurun_out/r2h_train_2gpu.err; tail -c 900 gpurun_out/r2h_train_2gpu.json; tail -3 gpurun_out/r2h_train_2gpu.err
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err; tail -c 1200 gpurun_out/r2h_bench.json; tail -3 gpurun_out/r2h_bench.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --no-extras > gpurun_out/r2h_bench_2gpu.json 2> gpurun_out/r2h_bench_2gpu.err; head -c 400 gpurun_out/r2h_bench_2gpu.json
+timeout 600 python tools/prof_train.py 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" > gpurun_out/r2k_prof_train.log; grep -n "plain step\|^step\|Self CUDA time" gpurun_out/r2k_prof_train.log; grep -n "hold::\|cutlass\|indexing\|Backward" gpurun_out/r2k_prof_train.log | head -30 | cut -c1-220
+timeout 900 python tools/bench_aux.py 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tee gpurun_out/r2k_bench_aux.log
+timeout 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_stages.py -q -x 2>&1 | tail -3

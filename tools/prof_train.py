@@ -17,10 +17,21 @@ inp = scene_io.scene_input(sc, dev)
 inp["uv"] = torch.gather(inp["uv"], 1, ids.to(dev)[:, :, None].expand(-1, -1, 2)).contiguous()
 R = Bf * px
 gt_rgb = torch.rand(R, 3, device=dev); gt_mask = torch.zeros(R, 4, device=dev); gt_mask[:, 0] = 1
+pose_leaves = []
+if os.environ.get("POSE_GRAD", "1") == "1":
+    for k in list(inp):
+        if torch.is_tensor(inp[k]) and inp[k].is_floating_point() and any(k.endswith(sfx) for sfx in (".full_pose", ".transl", ".global_orient")):
+            inp[k] = inp[k].clone().requires_grad_(True)
+            pose_leaves.append(inp[k])
 ts = train.TrainStep(net)
+ts.params = ts.params + pose_leaves
 for _ in range(2):
     ts.step(inp, gt_rgb, gt_mask)
 torch.cuda.synchronize()
+import time
+for i in range(3):
+    t0 = time.perf_counter(); ts.step(inp, gt_rgb, gt_mask); torch.cuda.synchronize()
+    print(f"plain step {i}: {1e3 * (time.perf_counter() - t0):.1f} ms (pose leaves: {len(pose_leaves)})")
 pr = cProfile.Profile(); pr.enable()
 for _ in range(3):
     ts.step(inp, gt_rgb, gt_mask)
@@ -32,3 +43,18 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as p:
     ts.step(inp, gt_rgb, gt_mask)
     torch.cuda.synchronize()
 print(p.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+
+# ---- allocator behaviour across steps
+import time
+for i in range(3):
+    s0 = torch.cuda.memory_stats()
+    t0 = time.perf_counter()
+    ts.step(inp, gt_rgb, gt_mask)
+    torch.cuda.synchronize()
+    s1 = torch.cuda.memory_stats()
+    print(f"step {i}: {1e3 * (time.perf_counter() - t0):.1f} ms; cudaMalloc calls {s1['num_device_alloc'] - s0['num_device_alloc']}, cudaFree calls {s1['num_device_free'] - s0['num_device_free']}, "
+          f"alloc retries {s1['num_alloc_retries'] - s0['num_alloc_retries']}, reserved {s1['reserved_bytes.all.current'] / 2**30:.1f} GiB, peak allocated {s1['allocated_bytes.all.peak'] / 2**30:.1f} GiB")
+t0 = time.perf_counter()
+xs = [torch.empty(125440, 256, device=dev) for _ in range(200)]
+torch.cuda.synchronize()
+print(f"200 x torch.empty(125440, 256): {1e3 * (time.perf_counter() - t0):.1f} ms")
