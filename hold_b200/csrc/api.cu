@@ -18,6 +18,7 @@
 #include "mise.cuh"
 #include "warp_bwd.cuh"
 #include "train.cuh"
+#include "wgrad_tc.cuh"
 
 namespace hold {
 
@@ -198,6 +199,7 @@ int hold_ctx_create(hold_ctx** out, int device) {
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_SDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   HOLD_CUDA(cudaFuncSetAttribute(k_bg_mlp<BG_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemBytes));
   int rc = tc_init(ctx);
+  if (rc == HOLD_OK) rc = wgrad_init();
   if (rc == HOLD_OK) rc = tc_bg_init();
   if (rc) { delete ctx; return rc; }
   *out = ctx;
@@ -1035,6 +1037,23 @@ int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda
   NodeState& ns = ctx->nodes[node];
   HOLD_REQUIRE(ns.tc != nullptr, "hold_linear needs the packed tcgen05 weight images (hold_node_set_weights)");
   return tc_launch_linear(ctx, ns, mat, P, A, lda, kvalid, add_bias, in_scale, C, ldc, nvalid, (cudaStream_t)stream);
+}
+
+int hold_wgrad(hold_ctx* ctx, int P, const float* D, int ldd, int N, const float* A, int lda, int K, const float* d_scale,
+               const float* a_scale, float* out, int ldo, void* stream) {
+  HOLD_REQUIRE(ctx && D && A && out, "NULL argument");
+  HOLD_REQUIRE(P >= 0 && N >= 1 && N <= 256 && K >= 1 && K <= 256 && ldd >= N && lda >= K && ldo >= K, "hold_wgrad: N, K in [1, 256]");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  HOLD_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)K * sizeof(float), N, s));
+  if (P == 0) return HOLD_OK;
+  WgArgs a;
+  a.P = P, a.N = N, a.K = K, a.ldd = ldd, a.lda = lda, a.ldo = ldo, a.D = D, a.A = A, a.d_scale = d_scale, a.a_scale = a_scale;
+  a.out = out, a.err = ctx->dev_err;
+  const int slabs = ceil_div(P, kWgPts);
+  k_wgrad_tc<<<min(slabs, ctx->sm_count), kWgThreads, kWgSmem, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
 }
 
 int hold_train_ew(hold_ctx* ctx, int op, int P, const hold_ew_args* args, void* stream) {

@@ -5,7 +5,8 @@ torch.autograd.Functions whose forward AND backward run the algebra of hold_b200
   * every product with a weight matrix: `hold_linear` — the tcgen05 split-precision GEMM (k_mlp_tc<MLP_LINEAR>) against the node's
     packed weight images (forward and transposed);
   * every pointwise step between them: `hold_train_ew` (hold_b200/csrc/train.cuh);
-  * the weight-gradient reductions dW = D^T A over the points: torch.matmul (a plain library GEMM, fp32, TF32 off);
+  * the weight-gradient reductions dW = D^T A over the points: `hold_wgrad` (k_wgrad_tc: tcgen05 with in-register transposition
+    of both operands, same split-precision arithmetic);
   * inverse skinning / rigid warp and the pose servers: the existing kernels and their backward twins (hold_inverse_warp_bwd,
     hold_mano_lbs_bwd, hold_object_tf_bwd).
 The second-order path of the reference (normals feed the colour net with create_graph=True) needs no double backward here:
@@ -24,6 +25,8 @@ import torch
 
 from . import capi, train_algo as T
 from .capi import EwArgs, NodePose, check, lib, ptr, stream_ptr
+
+WGRAD_TC = True   # weight-gradient reductions on hold_wgrad (tcgen05); False: torch.matmul (fp32 library GEMM), kept for A/B timing
 
 EW = dict(ACT=0, MUL=1, MULROW=2, U_DZ2=3, DZ=4, EMBED=5, EMBED_VJP=6, EMBED_JVP=7, RELU=8, RELU_BWD=9)
 
@@ -107,7 +110,21 @@ class CudaOps:
         return self._linear(49 + l, A, 256, 256, False)
 
     def wgrad(self, D, A):
-        return D.T @ A
+        """D^T A over the points: hold_wgrad (tcgen05, operands rescaled by powers of two) in blocks of <= 256 x 256."""
+        if not WGRAD_TC:
+            return D.T @ A
+        P, N = D.shape
+        K = A.shape[1]
+        assert D.stride(1) == 1 and A.stride(1) == 1
+        out = torch.empty(N, K, device=D.device)
+        p2 = lambda t: torch.exp2(torch.floor(torch.log2(t.detach().abs().amax().clamp_min(1e-30)))).reshape(1).float().contiguous()
+        sd, sa = p2(D), p2(A)
+        for n0 in range(0, N, 256):
+            for k0 in range(0, K, 256):
+                check(lib().hold_wgrad(self.node.ctx.h, P, C.c_void_p(D.data_ptr() + 4 * n0), D.stride(0), min(256, N - n0),
+                                       C.c_void_p(A.data_ptr() + 4 * k0), A.stride(0), min(256, K - k0), ptr(sd), ptr(sa),
+                                       C.c_void_p(out.data_ptr() + 4 * (n0 * K + k0)), K, stream_ptr()))
+        return out
 
     def colsum(self, D):
         return D.sum(0)

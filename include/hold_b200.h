@@ -265,6 +265,12 @@ int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const
 int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda, int kvalid, int add_bias, const float* in_scale,
                 float* C, int ldc, int nvalid, void* stream);
 
+/* Weight-gradient reduction over the points, out[n, k] = sum_p D[p, n] * A[p, k] (N, K <= 256; out [N, ldo] is overwritten), on
+ * tcgen05 with the same fp16 hi/lo split x 3 passes (hold_b200/csrc/wgrad_tc.cuh).  d_scale / a_scale: device scalars (powers of
+ * two, NULL = 1) by which D / A are divided before the split; the result is multiplied back. */
+int hold_wgrad(hold_ctx* ctx, int P, const float* D, int ldd, int N, const float* A, int lda, int K, const float* d_scale,
+               const float* a_scale, float* out, int ldo, void* stream);
+
 /* Pointwise steps of the training backward on [P, ld] fp32 matrices (hold_b200/csrc/train.cuh): op 0 ACT out0 = [softplus(z) | e],
  * out1 = softplus'(z); 1 MUL; 2 MULROW (in0 = one row); 3 U_DZ2 out0 = h s, out1 = h q softplus''(z); 4 DZ out0 = in0 in1 (+ in2);
  * 5 EMBED (aux = derivative order 0..2; in1 = BARF weights or NULL); 6 EMBED_VJP; 7 EMBED_JVP; 8 RELU; 9 RELU_BWD. */

@@ -28,6 +28,31 @@ def _params64(sd):
     return {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
 
 
+def test_wgrad_kernel(ctx):
+    """hold_wgrad: out = D^T A over the points against float64, ragged sizes (P not a multiple of the 32-point slab, N / K below
+    and above one 256-block), small-magnitude gradients."""
+    import ctypes as C
+    from hold_b200 import capi
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(1)
+    for P, N, K, mag in ((5000, 256, 256, 1.0), (4133, 217, 39, 1e-6), (777, 256, 302, 1e-3), (64, 3, 256, 1.0), (20000, 257, 256, 1e-4)):
+        D = (torch.randn(P, N, generator=g) * mag).to(dev)
+        A = torch.randn(P, K, generator=g).to(dev)
+        ref = D.double().T @ A.double()
+        out = torch.empty(N, K, device=dev)
+        p2 = lambda t: torch.exp2(torch.floor(torch.log2(t.abs().amax()))).reshape(1).float().contiguous()
+        sd, sa = p2(D), p2(A)
+        for n0 in range(0, N, 256):
+            for k0 in range(0, K, 256):
+                capi.check(capi.lib().hold_wgrad(ctx.h, P, C.c_void_p(D.data_ptr() + 4 * n0), N, min(256, N - n0), C.c_void_p(A.data_ptr() + 4 * k0), K,
+                                                 min(256, K - k0), capi.ptr(sd), capi.ptr(sa), C.c_void_p(out.data_ptr() + 4 * (n0 * K + k0)), K, capi.stream_ptr()))
+        ctx.check()
+        e = rel(out, ref)
+        print(f"wgrad P={P} N={N} K={K} mag={mag}: {e:.2e}")
+        assert e < 1e-5, f"P={P} N={N} K={K}: {e:.2e}"
+
+
 @pytest.mark.parametrize("nid", ["right", "object"])
 def test_sdf_net_function(env, ctx, nid):
     from hold_b200 import train
