@@ -210,7 +210,7 @@ def ncu_traffic_bytes():
 
 def run_train(args):
     """SURVEY C5 / BASELINE configs[4]: one training step = 10 frames x 128 pixels per rank (parser.py:26,87-89) through sampler ->
-    nodes in training mode (forward + backward incl. the second-order path) -> merge + integrate -> losses -> ONE flat-bucket
+    nodes in training mode (forward + backward incl. the second-order path) -> merge + integrate -> background -> losses -> ONE flat-bucket
     all-reduce of every gradient -> Adam.  Prints its own JSON line (metric: training rays/s); weak scaling (rays per rank fixed)."""
     import __graft_entry__ as g
 
@@ -233,7 +233,11 @@ def run_train(args):
     sc = synth.make_scene(H=H, W=W, S=S, nodes=NODES, B=Bf, seed=0)
     for nid in sc.node_ids:
         sc.beta[nid] = torch.tensor(BETA)
-    net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    from hold_b200.model import HOLDNet
+
+    fg = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+    net = HOLDNet(ctx, dict(fg.nodes), background=bg)      # the whole model: both nodes + the NeRF++ background
     gen = torch.Generator().manual_seed(100 + rank)
     ids = torch.stack([torch.randperm(H * W, generator=gen)[:px] for _ in range(Bf)])          # this rank's pixels of every frame
     inp = scene_io.scene_input(sc, dev)
@@ -280,7 +284,8 @@ def run_train(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4] / SURVEY C5: training step, {Bf} frames x {px} pixels per rank, right hand + object, 128 samples/ray, beta {BETA}",
                        "collective": f"one flat-bucket all-reduce of {n_grad} fp32 gradients per step (NCCL)" if world > 1 else "none (1 rank)",
-                       "losses": "L1 rgb + L2 semantics + eikonal (256 canonical samples per frame)", "mlp_mode": "tcgen05 fp16-split x3 (hold_linear) + cuBLAS fp32 weight-gradient GEMMs"},
+                       "losses": "L1 rgb + L2 semantics + eikonal (256 canonical samples per frame)", "model": "right hand + object + NeRF++ background (32 inverse-sphere samples/ray)",
+                       "mlp_mode": "tcgen05 fp16-split x3: hold_linear (activations), hold_wgrad (weight gradients); hold_composite_bwd"},
             "gpu_launches": ctx.launches - l0, "loss": float(loss), "loss_terms": {k: float(v) for k, v in parts.items()}}))
     if dist is not None:
         dist.destroy_process_group()

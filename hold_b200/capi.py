@@ -87,12 +87,14 @@ EXPORTS = {
     "hold_sampler_round": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [fp] * 11 + [C.POINTER(C.c_int32), C.c_void_p]),
     "hold_shade": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, C.POINTER(NodePose), C.POINTER(Factors), C.c_void_p]),
     "hold_composite": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Factors), C.POINTER(C.c_int32), C.POINTER(RenderOut), C.POINTER(RenderOut), C.c_void_p]),
+    "hold_composite_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Factors), C.POINTER(C.c_int32), C.POINTER(RenderOut), C.POINTER(RenderOut), C.POINTER(Factors), C.c_void_p]),
     "hold_render_fg": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, fp, fp, C.POINTER(NodePose), C.POINTER(Factors), C.POINTER(RenderOut), C.POINTER(RenderOut), fp, C.c_void_p]),
     "hold_bg_set_weights": (C.c_int, [C.c_void_p, C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.c_int, C.c_void_p]),
     "hold_background": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, fp, fp, C.c_void_p]),
     "hold_sdf_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_void_p]),
     "hold_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int, C.c_void_p]),
     "hold_wgrad": (C.c_int, [C.c_void_p, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_void_p]),
+    "hold_pow2_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, C.c_int, fp, C.c_void_p]),
     "hold_train_ew": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(EwArgs), C.c_void_p]),
     "hold_rgb_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp, C.c_void_p]),
     "hold_forward_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, fp, C.POINTER(NodePose), fp, fp, fp, C.c_void_p]),

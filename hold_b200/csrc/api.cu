@@ -715,6 +715,51 @@ int hold_composite(hold_ctx* ctx, int n, int R, int S, const hold_factors* facto
   return HOLD_OK;
 }
 
+int hold_composite_bwd(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors, const int32_t* class_ids_host,
+                       const hold_render_out* g_comp, const hold_render_out* g_per_node, const hold_factors* d_factors, void* stream) {
+  HOLD_REQUIRE(ctx && factors && class_ids_host && d_factors, "NULL argument");
+  HOLD_REQUIRE(n >= 1 && n <= HOLD_MAX_NODES, "n = %d out of [1,%d]", n, HOLD_MAX_NODES);
+  HOLD_REQUIRE(R >= 0 && S >= 2, "bad R/S");
+  HOLD_REQUIRE(g_comp != nullptr || g_per_node != nullptr, "no upstream gradient given");
+  if (R == 0) return HOLD_OK;
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int k = 0; k < n; ++k) {
+    HOLD_REQUIRE(factors[k].color && factors[k].normal && factors[k].density && factors[k].z_vals, "factors[%d] incomplete", k);
+    HOLD_REQUIRE(d_factors[k].color && d_factors[k].normal && d_factors[k].density, "d_factors[%d] needs color, normal, density", k);
+    HOLD_REQUIRE(class_ids_host[k] >= 0 && class_ids_host[k] < 4, "class id out of range");
+  }
+  bool written = false;
+  if (g_comp != nullptr) {
+    CompositeBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n, a.R = R, a.S = S;
+    for (int k = 0; k < n; ++k) {
+      a.color[k] = factors[k].color, a.normal[k] = factors[k].normal, a.density[k] = factors[k].density, a.z[k] = factors[k].z_vals;
+      a.class_id[k] = class_ids_host[k];
+      a.d_color[k] = d_factors[k].color, a.d_normal[k] = d_factors[k].normal, a.d_density[k] = d_factors[k].density;
+    }
+    a.g = *g_comp, a.drop_head = n - 1, a.drop_tail = n, a.single_zmax_last = 0, a.accumulate = 0;
+    k_composite_bwd<<<ceil_div(R, 128), 128, 0, s>>>(a);
+    HOLD_LAUNCH_CHECK(ctx);
+    written = true;
+  }
+  if (g_per_node != nullptr) {
+    for (int k = 0; k < n; ++k) {
+      CompositeBwdArgs b;
+      memset(&b, 0, sizeof(b));
+      b.n = 1, b.R = R, b.S = S;
+      b.color[0] = factors[k].color, b.normal[0] = factors[k].normal, b.density[0] = factors[k].density, b.z[0] = factors[k].z_vals;
+      b.class_id[0] = class_ids_host[k];
+      b.d_color[0] = d_factors[k].color, b.d_normal[0] = d_factors[k].normal, b.d_density[0] = d_factors[k].density;
+      b.g = g_per_node[k], b.drop_head = 0, b.drop_tail = 0, b.single_zmax_last = 1, b.accumulate = written ? 1 : 0;
+      k_composite_bwd<<<ceil_div(R, 128), 128, 0, s>>>(b);
+      HOLD_LAUNCH_CHECK(ctx);
+    }
+  }
+  return HOLD_OK;
+}
+
 int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, int B, const float* cam_loc,
                    const float* ray_dirs, const hold_node_pose* poses, const hold_factors* factors,
                    const hold_render_out* comp, const hold_render_out* per_node, int32_t* iters, void* stream) {
@@ -1029,14 +1074,36 @@ int hold_sdf_eval(hold_ctx* ctx, int node, int P, const float* x_c, const float*
 
 int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda, int kvalid, int add_bias, const float* in_scale,
                 float* C, int ldc, int nvalid, void* stream) {
-  int rc = check_node(ctx, node, true);
-  if (rc) return rc;
+  HOLD_REQUIRE(ctx != nullptr, "ctx is NULL");
   HOLD_REQUIRE(P >= 0, "negative P");
   if (P == 0) return HOLD_OK;
   HOLD_REQUIRE(A && C, "NULL argument");
-  NodeState& ns = ctx->nodes[node];
-  HOLD_REQUIRE(ns.tc != nullptr, "hold_linear needs the packed tcgen05 weight images (hold_node_set_weights)");
-  return tc_launch_linear(ctx, ns, mat, P, A, lda, kvalid, add_bias, in_scale, C, ldc, nvalid, (cudaStream_t)stream);
+  const uint8_t* img = nullptr;
+  const float* bias = nullptr;
+  int nst = 8, kmax = 256, nmax = 256;
+  if (node == -1) {   // the background nets (hold_bg_set_weights with HOLD_MLP_TC)
+    HOLD_CUDA(cudaSetDevice(ctx->device));
+    HOLD_REQUIRE(ctx->has_bg && ctx->bg_tc != nullptr, "hold_linear(node -1) needs tensor-core background weights (hold_bg_set_weights, HOLD_MLP_TC)");
+    const TcBg& t = *ctx->bg_tc;
+    constexpr int kIn = kBgEmbed + kBgFrame;   // lin0: 116 inputs; the skip at layer 4 re-feeds the 84 embedding columns (lin3: 172 outputs)
+    if (mat >= 0 && mat <= 8) { img = t.sdf_img[mat]; bias = ctx->bg_sdf.bias[mat]; nst = t.sdf_nst[mat]; kmax = (mat == 0) ? kIn : 256; nmax = (mat == 3) ? 256 - kBgEmbed : 256; }
+    else if (mat >= 16 && mat <= 24) { img = t.sdf_imgT[mat - 16]; kmax = (mat == 19) ? 256 - kBgEmbed : 256; nmax = (mat == 16) ? kIn : 256; }
+    else if (mat == 32) { img = t.rgb_img; bias = ctx->bg_rgb.bias[0]; nst = 10; kmax = 320; nmax = 128; }
+    else if (mat == 48 || mat == 49) { img = t.rgb_imgT[mat - 48]; kmax = 128; nmax = (mat == 49) ? 64 : 256; }
+  } else {
+    int rc = check_node(ctx, node, true);
+    if (rc) return rc;
+    NodeState& ns = ctx->nodes[node];
+    HOLD_REQUIRE(ns.tc != nullptr, "hold_linear needs the packed tcgen05 weight images (hold_node_set_weights)");
+    if (mat >= 0 && mat <= 8) { img = ns.tc->sdf_img[mat]; bias = ns.sdf.bias[mat]; nst = ns.tc->sdf_nst[mat]; kmax = (mat == 0) ? kEmbed : 256; nmax = ns.sdf.N[mat]; }
+    else if (mat >= 16 && mat <= 24) { img = ns.tc->sdf_imgT[mat - 16]; kmax = (mat - 16 == 3) ? kHidden - kEmbed : 256; nmax = (mat == 16) ? kEmbed : 256; }
+    else if (mat >= 32 && mat <= 35) { img = ns.tc->rgb_img[mat - 32]; bias = ns.rgb.bias[mat - 32]; nst = ns.tc->rgb_nst[mat - 32]; kmax = (mat == 32) ? 320 : 256; }
+    else if (mat >= 48 && mat <= 52) { img = ns.tc->rgb_imgT[mat - 48]; nmax = (mat == 49) ? 64 : 256; }
+  }
+  HOLD_REQUIRE(img != nullptr, "hold_linear: unknown matrix id %d for node %d", mat, node);
+  HOLD_REQUIRE(kvalid >= 1 && kvalid <= kmax && nvalid >= 1 && nvalid <= nmax, "hold_linear(%d): kvalid %d (max %d) / nvalid %d (max %d)", mat, kvalid, kmax, nvalid, nmax);
+  HOLD_REQUIRE(!add_bias || bias != nullptr, "hold_linear(%d): this matrix has no bias", mat);
+  return tc_launch_linear_img(ctx, img, add_bias ? bias : nullptr, nst, P, A, lda, kvalid, in_scale, C, ldc, nvalid, (cudaStream_t)stream);
 }
 
 int hold_wgrad(hold_ctx* ctx, int P, const float* D, int ldd, int N, const float* A, int lda, int K, const float* d_scale,
@@ -1052,6 +1119,25 @@ int hold_wgrad(hold_ctx* ctx, int P, const float* D, int ldd, int N, const float
   a.out = out, a.err = ctx->dev_err;
   const int slabs = ceil_div(P, kWgPts);
   k_wgrad_tc<<<min(slabs, ctx->sm_count), kWgThreads, kWgSmem, s>>>(a);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_pow2_scale(hold_ctx* ctx, int P, int ncols, const float* x, int ld, float* scale_out, void* stream) {
+  HOLD_REQUIRE(ctx && x && scale_out, "NULL argument");
+  HOLD_REQUIRE(P >= 1 && ncols >= 1 && ld >= ncols, "bad sizes");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  void* w = nullptr;
+  int rc = ws_get(ctx, 21 /* WS_AMAX */, 256, &w);
+  if (rc) return rc;
+  // one word per call, rotating through the workspace so that back-to-back calls on a stream never share a counter in flight
+  unsigned int* bits = (unsigned int*)w + (ctx->launches & 31);
+  HOLD_CUDA(cudaMemsetAsync(bits, 0, sizeof(unsigned int), s));
+  const size_t total = (size_t)P * ncols;
+  k_absmax_bits<<<(int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, s>>>(P, ncols, x, ld, bits);
+  HOLD_LAUNCH_CHECK(ctx);
+  k_pow2_scale<<<1, 1, 0, s>>>(bits, scale_out);
   HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }

@@ -13,6 +13,8 @@ struct TcBg {
   int sdf_nst[9] = {0};
   uint8_t* rgb_img = nullptr;
   float* rgb_w_last = nullptr;   // [3][256]: lin1 rows padded from 128 to 256 columns with zeros
+  uint8_t* sdf_imgT[9] = {nullptr};   // training backward: W_l^T of the 9 layers (l = 8: the feature rows)
+  uint8_t* rgb_imgT[2] = {nullptr};   // colour lin0^T: to the 256 feature inputs / to [view (27) | frame code (32)]
 };
 
 __global__ void k_pad_rows(const float* __restrict__ src, int rows, int n_src, int n_dst, float* __restrict__ dst) {
@@ -24,7 +26,8 @@ __global__ void k_pad_rows(const float* __restrict__ src, int rows, int n_src, i
 
 static void tc_bg_free(TcBg*& t) {
   if (!t) return;
-  for (int l = 0; l < 9; ++l) cudaFree(t->sdf_img[l]);
+  for (int l = 0; l < 9; ++l) { cudaFree(t->sdf_img[l]); cudaFree(t->sdf_imgT[l]); }
+  cudaFree(t->rgb_imgT[0]), cudaFree(t->rgb_imgT[1]);
   cudaFree(t->rgb_img), cudaFree(t->rgb_w_last);
   delete t;
   t = nullptr;
@@ -54,6 +57,18 @@ static int tc_bg_pack(hold_ctx* ctx, TcBg*& tp, const hold_mlp_weights* sdf, con
   if (!t.rgb_img) HOLD_CUDA(cudaMalloc((void**)&t.rgb_img, (size_t)10 * kTcStageBytes));
   k_tc_pack<<<256, 128, 0, s>>>(rgb->weight_v[0], nullptr, K0, 0, 128, K0, 320, 1.0f, kBgView + kBgFrame, t.rgb_img);
   HOLD_LAUNCH_CHECK(ctx);
+  for (int l = 0; l < 9; ++l) {   // transposed images for the training backward (hold_linear, node = -1)
+    const int K_in = (l == 0) ? kBgEmbed + kBgFrame : kHidden, N_out = (l == 3) ? kHidden - kBgEmbed : kHidden;
+    if (!t.sdf_imgT[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgT[l], (size_t)8 * kTcStageBytes));
+    const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
+    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], nullptr, sdf->in_dim[l], l == 8 ? 1 : 0, N_out, K_in, 0, 0, scale, t.sdf_imgT[l]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!t.rgb_imgT[i]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_imgT[i], (size_t)8 * kTcStageBytes));
+    k_tc_pack_T<<<256, 256, 0, s>>>(rgb->weight_v[0], nullptr, K0, 0, 128, K0, i == 0 ? 1 : 2, kBgView + kBgFrame, 1.0f, t.rgb_imgT[i]);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
   if (!t.rgb_w_last) HOLD_CUDA(cudaMalloc((void**)&t.rgb_w_last, 3 * 256 * sizeof(float)));
   k_pad_rows<<<3, 256, 0, s>>>(ctx->bg_rgb.w_last, 3, 128, 256, t.rgb_w_last);
   HOLD_LAUNCH_CHECK(ctx);

@@ -890,16 +890,18 @@ __global__ void k_tc_pack(const float* __restrict__ v, const float* __restrict__
 
 // Transposed image for the reverse-mode gradient: B rows = input index k_in of layer l, K = output index n_out:
 // WT[r][n_out] = kTcScaleW * scale * fold(v, g)[row_off + n_out][src(r)]  (zero outside [N_out) x valid sources).
-// colmap: 0: src = r (r < K_in);  1: colour lin0, feature part: src = 14 + r (r < 256);
-//         2: colour lin0, other inputs in the A operand's order [x_c, n, pose (14) | time code (32)]: src = r (r < 14), 256 + r (r < K_in - 256)
+// colmap: 0: src = r (r < K_in);  1: a first layer whose 256 feature inputs follow `lead` other inputs (colour lin0: lead = 14 [x_c, n,
+//         pose]; background colour lin0: lead = 59 [view, frame code]), feature part: src = lead + r (r < 256);
+//         2: the same layer's other inputs in the A operand's order [leading inputs | inputs after the features]: src = r (r < lead),
+//         256 + r (256 + r < K_in)
 __global__ void k_tc_pack_T(const float* __restrict__ v, const float* __restrict__ g, int in_dim, int row_off, int N_out, int K_in,
-                            int colmap, float scale, uint8_t* __restrict__ img) {
+                            int colmap, int lead, float scale, uint8_t* __restrict__ img) {
   const int r = blockIdx.x;   // k_in, 0..255
   const int n = threadIdx.x;  // n_out, 0..255
   int src = -1;
   if (colmap == 0) src = (r < K_in) ? r : -1;
-  else if (colmap == 1) src = 14 + r;
-  else src = (r < 14) ? r : ((256 + r < K_in) ? 256 + r : -1);
+  else if (colmap == 1) src = lead + r;
+  else src = (r < lead) ? r : ((256 + r < K_in) ? 256 + r : -1);
   float w = 0.f;
   if (n < N_out && src >= 0) {
     const float* vr = v + (size_t)(row_off + n) * in_dim;
@@ -958,13 +960,13 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
     const int K_in = (l == 0) ? kEmbed : kHidden, N_out = (l == 3) ? kHidden - kEmbed : kHidden;
     if (!t.sdf_imgT[l]) HOLD_CUDA(cudaMalloc((void**)&t.sdf_imgT[l], (size_t)8 * kTcStageBytes));
     const float scale = (l == 4) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
-    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], l == 8 ? 1 : 0, N_out, K_in, 0, scale, t.sdf_imgT[l]);
+    k_tc_pack_T<<<256, 256, 0, s>>>(sdf->weight_v[l], sdf->weight_g[l], sdf->in_dim[l], l == 8 ? 1 : 0, N_out, K_in, 0, 0, scale, t.sdf_imgT[l]);
     HOLD_LAUNCH_CHECK(ctx);
   }
   for (int i = 0; i < 5; ++i) {  // colour net transposes for the training backward: lin0 in two parts (its K = 320 > 256), lin1..3
     const int l = (i < 2) ? 0 : i - 1;
     if (!t.rgb_imgT[i]) HOLD_CUDA(cudaMalloc((void**)&t.rgb_imgT[i], (size_t)8 * kTcStageBytes));
-    k_tc_pack_T<<<256, 256, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, rgb->in_dim[l], i == 0 ? 1 : (i == 1 ? 2 : 0), 1.0f,
+    k_tc_pack_T<<<256, 256, 0, s>>>(rgb->weight_v[l], rgb->weight_g[l], rgb->in_dim[l], 0, 256, rgb->in_dim[l], i == 0 ? 1 : (i == 1 ? 2 : 0), 14, 1.0f,
                                     t.rgb_imgT[i]);
     HOLD_LAUNCH_CHECK(ctx);
   }
@@ -1011,24 +1013,14 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   return HOLD_OK;
 }
 
-// hold_linear: C[P, nvalid] = A[P, kvalid] . M^T (+ bias) for one packed matrix M of the node (see include/hold_b200.h for `mat`)
-static int tc_launch_linear(hold_ctx* ctx, NodeState& ns, int mat, int P, const float* A, int lda, int kvalid, int add_bias,
-                            const float* in_scale, float* Cout, int ldc, int nvalid, cudaStream_t s) {
+// hold_linear: C[P, nvalid] = A[P, kvalid] . M^T (+ bias) against one packed image (selection of the image: api.cu)
+static int tc_launch_linear_img(hold_ctx* ctx, const uint8_t* img, const float* bias, int nst, int P, const float* A, int lda, int kvalid,
+                                const float* in_scale, float* Cout, int ldc, int nvalid, cudaStream_t s) {
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.P = P, a.n_layers = 1;
-  const uint8_t* img = nullptr;
-  const float* bias = nullptr;
-  int nst = 8, kmax = 256, nmax = 256;
-  if (mat >= 0 && mat <= 8) { img = ns.tc->sdf_img[mat]; bias = ns.sdf.bias[mat]; nst = ns.tc->sdf_nst[mat]; kmax = (mat == 0) ? kEmbed : 256; nmax = ns.sdf.N[mat]; }
-  else if (mat >= 16 && mat <= 24) { img = ns.tc->sdf_imgT[mat - 16]; kmax = (mat - 16 == 3) ? kHidden - kEmbed : 256; nmax = (mat == 16) ? kEmbed : 256; }
-  else if (mat >= 32 && mat <= 35) { img = ns.tc->rgb_img[mat - 32]; bias = ns.rgb.bias[mat - 32]; nst = ns.tc->rgb_nst[mat - 32]; kmax = (mat == 32) ? 320 : 256; }
-  else if (mat >= 48 && mat <= 52) { img = ns.tc->rgb_imgT[mat - 48]; nmax = (mat == 49) ? 64 : 256; }
-  HOLD_REQUIRE(img != nullptr, "hold_linear: unknown matrix id %d", mat);
-  HOLD_REQUIRE(kvalid >= 1 && kvalid <= kmax && nvalid >= 1 && nvalid <= nmax, "hold_linear(%d): kvalid %d (max %d) / nvalid %d (max %d)", mat, kvalid, kmax, nvalid, nmax);
   HOLD_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Cout & 15) == 0, "hold_linear: rows must be 16-byte aligned");
-  HOLD_REQUIRE(!add_bias || bias != nullptr, "hold_linear(%d): this matrix has no bias", mat);
-  a.L[0].wimg = img, a.L[0].bias = add_bias ? bias : nullptr, a.L[0].nst = nst, a.L[0].N = nvalid;
+  a.L[0].wimg = img, a.L[0].bias = bias, a.L[0].nst = nst, a.L[0].N = nvalid;
   a.passes = 3;
   a.lin_in = A, a.lda = lda, a.kvalid = kvalid, a.lin_out = Cout, a.ldc = ldc, a.nvalid = nvalid, a.in_scale = in_scale;
   a.err = ctx->dev_err, a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));

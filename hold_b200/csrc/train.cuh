@@ -30,7 +30,8 @@ __device__ __forceinline__ float embed_comp(int e, float t, int order) {
 }
 
 __global__ void __launch_bounds__(256) k_train_ew(int op, int P, EwArgs a) {
-  const size_t total = (size_t)P * (size_t)((op == EW_EMBED_VJP) ? 3 : ((op == EW_ACT && a.in1 != nullptr) ? a.ncols + kEmbed : a.ncols));
+  // EW_ACT with a skip operand: `aux` appended columns (0 = the 39 embedding columns of the foreground SDF net)
+  const size_t total = (size_t)P * (size_t)((op == EW_EMBED_VJP) ? 3 : ((op == EW_ACT && a.in1 != nullptr) ? a.ncols + (a.aux > 0 ? a.aux : kEmbed) : a.ncols));
   const int width = (int)(total / (size_t)P);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t p = i / width;
@@ -73,6 +74,25 @@ __global__ void __launch_bounds__(256) k_train_ew(int op, int P, EwArgs a) {
       default: break;
     }
   }
+}
+
+// Power-of-two scale of a matrix for the operand rescaling of hold_linear / hold_wgrad: 2^floor(log2(max |x|)) (1e-30 floor).
+__global__ void __launch_bounds__(256) k_absmax_bits(int P, int ncols, const float* __restrict__ x, int ld, unsigned int* __restrict__ bits) {
+  const size_t total = (size_t)P * ncols;
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i / ncols;
+    m = fmaxf(m, fabsf(x[p * ld + (i - p * ncols)]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+__global__ void k_pow2_scale(const unsigned int* __restrict__ bits, float* __restrict__ out) {
+  const float m = fmaxf(__uint_as_float(*bits), 1e-30f);
+  int e;
+  frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)  ->  2^floor(log2 m) = 2^(e-1)
+  *out = ldexpf(1.0f, e - 1);
 }
 
 }  // namespace hold

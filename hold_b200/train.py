@@ -69,12 +69,16 @@ class CudaOps:
         P = A.shape[0]
         assert A.stride(1) == 1 and A.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0, "hold_linear wants 16-byte aligned rows"
         out = torch.empty(P, out_cols, device=A.device)
-        sc = None
-        if self.scaled:
-            sc = torch.exp2(torch.floor(torch.log2(A.detach().abs().amax().clamp_min(1e-30)))).reshape(1).float().contiguous()
+        sc = self._scale(A) if self.scaled else None
         check(lib().hold_linear(self.node.ctx.h, self.node.slot, mat, P, ptr(A) if A.is_contiguous() else C.c_void_p(A.data_ptr()), A.stride(0),
                                 kvalid, 1 if bias else 0, ptr(sc), C.c_void_p(out.data_ptr()), out.stride(0), nvalid, stream_ptr()))
         return out[:, :nvalid]
+
+    def _scale(self, t):
+        """device scalar 2^floor(log2 max|t|) (hold_pow2_scale: two small launches, no host sync)"""
+        sc = torch.empty(1, device=t.device)
+        check(lib().hold_pow2_scale(self.node.ctx.h, t.shape[0], t.shape[1], C.c_void_p(t.data_ptr()), t.stride(0), ptr(sc), stream_ptr()))
+        return sc
 
     def lin(self, A, l, bias=True):
         if self.net == "sdf":
@@ -117,8 +121,7 @@ class CudaOps:
         K = A.shape[1]
         assert D.stride(1) == 1 and A.stride(1) == 1
         out = torch.empty(N, K, device=D.device)
-        p2 = lambda t: torch.exp2(torch.floor(torch.log2(t.detach().abs().amax().clamp_min(1e-30)))).reshape(1).float().contiguous()
-        sd, sa = p2(D), p2(A)
+        sd, sa = self._scale(D), self._scale(A)
         for n0 in range(0, N, 256):
             for k0 in range(0, K, 256):
                 check(lib().hold_wgrad(self.node.ctx.h, P, C.c_void_p(D.data_ptr() + 4 * n0), D.stride(0), min(256, N - n0),
@@ -136,8 +139,8 @@ class CudaOps:
     def act(self, z, e=None):
         P, n = z.shape
         a, s = torch.empty(P, 256, device=z.device), torch.empty(P, 256, device=z.device)
-        _ew(self.node, EW["ACT"], P, n, z, e, None, a, s)
-        return (a[:, :n] if e is None else a), s[:, :n]
+        _ew(self.node, EW["ACT"], P, n, z, e, None, a, s, aux=0 if e is None else e.shape[1])
+        return (a[:, :n] if e is None else a[:, :n + e.shape[1]]), s[:, :n]
 
     def _binary(self, op, x, y, in2=None, ld2=None, two=False):
         P, n = y.shape
@@ -365,6 +368,196 @@ def merge_factors(fl):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ background (renderables/background.py)
+class _BgHandle:
+    """What CudaOps needs from a "node" when the matrices are the background's (hold_linear with node = -1)."""
+
+    def __init__(self, ctx):
+        self.ctx, self.slot, self.kind = ctx, -1, "background"
+
+
+class BgOps(CudaOps):
+    """train_algo backend for the background nets: net = "bg_sdf" (9 plain layers, 116 inputs, skip at 4) | "bg_rgb" (315 -> 128 -> 3)."""
+
+    def __init__(self, ctx, net, W, b):
+        super().__init__(_BgHandle(ctx), net, W, b)
+
+    def lin(self, A, l, bias=True):
+        if self.net == "bg_sdf":
+            if l == 8:
+                feat = self._linear(8, A, 256, 256, bias)
+                head = A @ self.W[8][0] + (self.b[8][0] if bias else 0.0)
+                return torch.cat([head[:, None], feat], 1)
+            return self._linear(l, A, A.shape[1], 172 if l == 3 else 256, bias)
+        if l == 1:       # 128 -> 3 head
+            y = A @ self.W[1].T
+            return y + self.b[1] if bias else y
+        A = torch.cat([A[:, 59:], A[:, :59], A.new_zeros(A.shape[0], 5)], 1)      # operand order [feature (256) | view, frame (59)] + pad
+        return self._linear(32, A, 320, 128, bias)
+
+    def lin_t(self, A, l):
+        if self.net == "bg_sdf":
+            if l == 8:
+                return A[:, :1] * self.W[8][0][None, :] + self._linear(24, A[:, 1:].contiguous(), 256, 256, False)
+            if l == 0:
+                return self._linear(16, A, 256, 116, False, out_cols=116)
+            return self._linear(16 + l, A, A.shape[1], 256, False)
+        if l == 1:
+            return A @ self.W[1]
+        f = self._linear(48, A, 128, 256, False)
+        o = self._linear(49, A, 128, 64, False, out_cols=64)
+        return torch.cat([o[:, :59], f], 1)
+
+
+class BgSdfFn(torch.autograd.Function):
+    """out [P,257] = bg_implicit_network([PE-10(point) | frame code]); differentiable w.r.t. the input rows (frame code) and weights."""
+
+    @staticmethod
+    def forward(fctx, ctx, inp, *Wb):
+        W, b = [w.detach().float() for w in Wb[:9]], [v.detach().float() for v in Wb[9:]]
+        ops = BgOps(ctx, "bg_sdf", W, b)
+        out, st = T.skipnet_forward(ops, inp.detach().float().contiguous(), skip=4, d_skip=84)
+        fctx.ops, fctx.st = ops, st
+        return out
+
+    @staticmethod
+    def backward(fctx, d_out):
+        fctx.ops.scaled = True
+        d_inp, dW, db = T.skipnet_backward(fctx.ops, fctx.st, d_out.float().contiguous())
+        dW[4] = dW[4] * (1.0 / math.sqrt(2.0))
+        return (None, d_inp, *dW, *db)
+
+
+class BgRgbFn(torch.autograd.Function):
+    """rgb [P,3] = bg_rendering_network([view PE-4 | frame code | feature]) (texture_net.py:55-68,95-101)."""
+
+    @staticmethod
+    def forward(fctx, ctx, inp, W0, W1, b0, b1):
+        ops = BgOps(ctx, "bg_rgb", [W0.detach().float(), W1.detach().float()], [b0.detach().float(), b1.detach().float()])
+        rgb, st = T.head_forward(ops, inp.detach().float().contiguous())
+        fctx.ops, fctx.st = ops, st
+        return rgb
+
+    @staticmethod
+    def backward(fctx, d_rgb):
+        fctx.ops.scaled = True
+        d_in, dW, db = T.head_backward(fctx.ops, fctx.st, d_rgb.float().contiguous())
+        return (None, d_in, dW[0], dW[1], db[0], db[1])
+
+
+def _embed_n(x, n_freq):
+    out = [x]
+    for k in range(n_freq):
+        f = float(2.0 ** k)
+        out += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(out, -1)
+
+
+def depth2pts_outside(ray_o, ray_d, depth, R_s):
+    """Background.depth2pts_outside (background.py:102-135), torch (no parameters reach it)."""
+    o_dot_d = (ray_d * ray_o).sum(-1)
+    under = o_dot_d ** 2 - ((ray_o ** 2).sum(-1) - R_s ** 2)
+    d_sphere = torch.sqrt(under) - o_dot_d
+    p_sphere = ray_o + d_sphere[..., None] * ray_d
+    p_mid = ray_o - o_dot_d[..., None] * ray_d
+    pmn = torch.norm(p_mid, dim=-1)
+    axis = torch.cross(ray_o, p_sphere, dim=-1)
+    axis = axis / torch.norm(axis, dim=-1, keepdim=True)
+    ang = (torch.asin(pmn / R_s) - torch.asin(pmn * depth))[..., None]
+    pn = p_sphere * torch.cos(ang) + torch.cross(axis, p_sphere, dim=-1) * torch.sin(ang) + axis * (axis * p_sphere).sum(-1, keepdim=True) * (1.0 - torch.cos(ang))
+    pn = pn / torch.norm(pn, dim=-1, keepdim=True)
+    return torch.cat([pn, depth[..., None]], -1)
+
+
+def background_forward_train(bg, fg_bg_weights, ray_dirs, cam_loc, idx, B, R_s, n_bg=32, sync=True):
+    """Background.forward in training (background.py:35-100): -> dict(bg_rgb = bg_weights * bg_rgb_only, bg_rgb_only, bg_semantics),
+    differentiable w.r.t. the background nets, its frame codes and the foreground's bg_weights.  Eval-mode (deterministic) inverse
+    sphere samples; the nets run on hold_linear (node -1), their weights must have been packed in tensor-core mode."""
+    if sync:
+        bg.sync_weights()
+    R = ray_dirs.shape[0]
+    dev = ray_dirs.device
+    z = torch.flip(torch.linspace(0.0, 1.0, n_bg, device=dev) * (1.0 / R_s), dims=[-1])[None].expand(R, n_bg)       # 1/R_s ... 0
+    pts = depth2pts_outside(cam_loc[:, None, :].expand(R, n_bg, 3), ray_dirs[:, None, :].expand(R, n_bg, 3), z, R_s).reshape(R * n_bg, 4)
+    fc = bg.frame_latent_encoder(idx)                                                                                  # [B,32]
+    fcp = fc[:, None, :].expand(B, (R // B) * n_bg, 32).reshape(R * n_bg, 32)
+    inp = torch.cat([_embed_n(pts, 10), fcp], 1)
+    Ws = [getattr(bg.bg_implicit_network, f"lin{l}").weight for l in range(9)]
+    bs = [getattr(bg.bg_implicit_network, f"lin{l}").bias for l in range(9)]
+    out = BgSdfFn.apply(bg.ctx, inp, *Ws, *bs)
+    sdf, feat = out[:, 0], out[:, 1:]
+    view = _embed_n(ray_dirs[:, None, :].expand(R, n_bg, 3).reshape(R * n_bg, 3), 4)
+    rn = bg.bg_rendering_network
+    rgb = BgRgbFn.apply(bg.ctx, torch.cat([view, fcp, feat], 1), rn.lin0.weight, rn.lin1.weight, rn.lin0.bias, rn.lin1.bias).reshape(R, n_bg, 3)
+    dens = sdf.abs().reshape(R, n_bg)                                                                                  # AbsDensity (density.py:33-35)
+    dists = torch.cat([z[:, :-1] - z[:, 1:], torch.full((R, 1), 1e10, device=dev)], -1)
+    fe = dists * dens
+    w = (1 - torch.exp(-fe)) * torch.exp(-torch.cumsum(torch.cat([torch.zeros(R, 1, device=dev), fe[:, :-1]], -1), -1))
+    only = (w[:, :, None] * rgb).sum(1)
+    sem = torch.zeros(R, 4, device=dev)
+    sem[:, 0] = 1.0
+    return dict(bg_rgb=fg_bg_weights[:, None] * only, bg_rgb_only=only, bg_semantics=fg_bg_weights[:, None] * sem)
+
+
+class CompositeFn(torch.autograd.Function):
+    """merge_factors + volumetric_render of the scene (hold_net.py:76-88) on hold_composite / hold_composite_bwd.
+    inputs: per node color [R,S,3], normal [R,S,3], density [R,S] (differentiable), z_vals [R,S]; class ids.
+    -> fg_rgb [R,3], mask_prob [R], normal [R,3], depth [R], fg_semantics [R,4], bg_weights [R]."""
+
+    @staticmethod
+    def forward(fctx, ctx_h, class_ids, n, *tensors):
+        from .capi import Factors, RenderOut
+
+        cols, nrms, dens, zs = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n], tensors[3 * n:4 * n]
+        R, S = zs[0].shape
+        dev = zs[0].device
+        f = lambda t: t.detach().float().contiguous()
+        keep = [[f(cols[k]), f(nrms[k]), f(dens[k]), f(zs[k])] for k in range(n)]
+        facs = (Factors * n)()
+        for k in range(n):
+            facs[k].color, facs[k].normal, facs[k].density, facs[k].z_vals = (t.data_ptr() for t in keep[k])
+        out = dict(fg_rgb=torch.empty(R, 3, device=dev), mask_prob=torch.empty(R, device=dev), normal=torch.empty(R, 3, device=dev),
+                   depth=torch.empty(R, device=dev), fg_semantics=torch.empty(R, 4, device=dev), bg_weights=torch.empty(R, device=dev))
+        ro = RenderOut()
+        for kk, v in out.items():
+            setattr(ro, kk, v.data_ptr())
+        cls = (C.c_int32 * n)(*class_ids)
+        check(lib().hold_composite(ctx_h, n, R, S, facs, cls, C.byref(ro), None, stream_ptr()))
+        fctx.ctx_h, fctx.cls, fctx.n, fctx.keep, fctx.facs = ctx_h, cls, n, keep, facs
+        return tuple(out[k] for k in ("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights"))
+
+    @staticmethod
+    def backward(fctx, *gs):
+        from .capi import Factors, RenderOut
+
+        n, keep = fctx.n, fctx.keep
+        R, S = keep[0][3].shape
+        dev = keep[0][3].device
+        g = RenderOut()
+        hold = []
+        for name, t in zip(("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights"), gs):
+            if t is not None:
+                t = t.float().contiguous()
+                hold.append(t)
+                setattr(g, name, t.data_ptr())
+        d = [[torch.empty(R, S, 3, device=dev), torch.empty(R, S, 3, device=dev), torch.empty(R, S, device=dev)] for _ in range(n)]
+        dfac = (Factors * n)()
+        for k in range(n):
+            dfac[k].color, dfac[k].normal, dfac[k].density = (t.data_ptr() for t in d[k])
+        check(lib().hold_composite_bwd(fctx.ctx_h, n, R, S, fctx.facs, fctx.cls, C.byref(g), None, dfac, stream_ptr()))
+        return (None, None, None, *[d[k][0] for k in range(n)], *[d[k][1] for k in range(n)], *[d[k][2] for k in range(n)], *([None] * n))
+
+
+def composite(ctx, factors, class_ids):
+    """dict(fg_rgb, mask_prob, normal, depth, fg_semantics, bg_weights) of the scene's factors (list of dicts with color, normal,
+    density, z_vals), differentiable w.r.t. color / normal / density."""
+    n = len(factors)
+    fctx_set = lambda fn: fn
+    outs = CompositeFn.apply(ctx.h, list(class_ids), n, *[f["color"] for f in factors], *[f["normal"] for f in factors],
+                             *[f["density"] for f in factors], *[f["z_vals"] for f in factors])
+    return dict(zip(("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights"), outs))
+
+
 class TrainStep:
     """One data-parallel training step of the foreground model (hold/hold.py:110-137 without the Lightning plumbing): every
     rank takes its share of the step's rays, runs sampler (no grad) -> nodes in training mode -> merge + integrate -> losses,
@@ -402,19 +595,21 @@ class TrainStep:
             o = node_forward_train(node, x, srv["tfs"] if hand else tfs, srv["verts"] if hand else None, frp,
                                    pose_cond=(input[f"{node.node_id}.full_pose"][:, 3:] / math.pi) if hand else None,
                                    time_code=None if hand else node.frame_latent_encoder(input["idx"]), sync=False)
-            sem = torch.zeros(B * P, S, 4, device=dev)
-            sem[:, :, node.class_id] = 1.0
             factors.append(dict(color=o["color"].reshape(B * P, S, 3), normal=o["normal"].reshape(B * P, S, 3),
-                                density=o["density"].reshape(B * P, S), semantics=sem, z_vals=z))
+                                density=o["density"].reshape(B * P, S), z_vals=z))
             # eikonal samples: uniform in [-0.3, 0.3]^3 (volsdf_utils.py:38-42), gradient through the same function
             xs = (torch.rand(B * self.n_eik, 3, device=dev, generator=generator) * 0.6 - 0.3)
             Ws, bs = _folded_sdf(node)
             _, _, ge = SdfNetFn.apply(node, xs, *Ws, *bs)
             eik.append(((ge.norm(2, dim=-1) - 1) ** 2).mean())
-        comp = volumetric_render(merge_factors(factors))
+        comp = composite(net.ctx, factors, [nd.class_id for nd in net.nodes.values()])     # hold_composite / hold_composite_bwd
+        rgb, sem = comp["fg_rgb"], comp["fg_semantics"]
+        if getattr(net, "background", None) is not None:                                    # hold_net.py:110-134: rgb = fg + bg_weights * bg
+            bgo = background_forward_train(net.background, comp["bg_weights"], dirs, cam, input["idx"], B, next(iter(net.nodes.values())).bounding_sphere)
+            rgb, sem = rgb + bgo["bg_rgb"], sem + bgo["bg_semantics"]
         valid = gt_rgb.shape[0]
-        loss_rgb = (comp["fg_rgb"] - gt_rgb).abs().sum() / (valid + 1e-6)
-        loss_sem = ((comp["fg_semantics"] - gt_mask) ** 2).mean()
+        loss_rgb = (rgb - gt_rgb).abs().sum() / (valid + 1e-6)
+        loss_sem = ((sem - gt_mask) ** 2).mean()
         loss_eik = sum(eik) * 1e-5
         return loss_rgb + loss_sem + loss_eik, dict(rgb=loss_rgb.detach(), sem=loss_sem.detach(), eikonal=loss_eik.detach())
 

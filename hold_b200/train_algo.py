@@ -220,3 +220,52 @@ def rgb_backward(ops, st, d_rgb):
         dW[l], db[l] = ops.wgrad(dz, A[l]), ops.colsum(dz)
         dA = ops.lin_t(dz, l)
     return dA, dW, db
+
+
+# ------------------------------------------------------------------------------------------------ background nets (renderables/background.py)
+def skipnet_forward(ops, inp, skip=4, d_skip=None):
+    """A Softplus(100) chain with one skip connection and no input gradient output (the NeRF++ background's implicit net,
+    confs/general.yaml:34-54; shape_net.py:116-126): A_0 = inp [P, d_in] = [e | cond];  z_l = A_l W_l^T + b_l;  A_{l+1} = softplus(z_l),
+    A_skip = [a | e] with e = the first d_skip columns of inp (the embedding; the 1/sqrt 2 lives in W_skip);  out = A_8 W_8^T + b_8."""
+    d_skip = inp.shape[1] if d_skip is None else d_skip
+    e = inp[:, :d_skip]
+    A, S = [inp], []
+    for l in range(8):
+        a, s = ops.act(ops.lin(A[l], l), e if l + 1 == skip else None)
+        S.append(s)
+        A.append(a)
+    return ops.lin(A[8], 8), dict(A=A, S=S, skip=skip, d_skip=d_skip)
+
+
+def skipnet_backward(ops, st, d_out):
+    """-> d_inp [P, d_in], dW[0..8], db[0..8] (dW[skip] w.r.t. the matrix `ops` holds, W_skip / sqrt 2)."""
+    A, S, skip, d_skip = st["A"], st["S"], st["skip"], st["d_skip"]
+    dW, db = [None] * 9, [None] * 9
+    dW[8], db[8] = ops.wgrad(d_out, A[8]), ops.colsum(d_out)
+    dA = ops.lin_t(d_out, 8)
+    d_e = None
+    for l in range(7, -1, -1):
+        dz = ops.dz(dA, S[l], None)
+        dW[l], db[l] = ops.wgrad(dz, A[l]), ops.colsum(dz)
+        dA = ops.lin_t(dz, l)
+        if l == skip:
+            n_a = dA.shape[1] - d_skip
+            d_e, dA = dA[:, n_a:], dA[:, :n_a]
+    d_inp = dA.clone() if d_e is None else torch.cat([dA[:, :d_skip] + d_e, dA[:, d_skip:]], 1)
+    return d_inp, dW, db
+
+
+def head_forward(ops, inp):
+    """ReLU layer + 3-row sigmoid head (the background's colour net, 315 -> 128 -> 3)."""
+    a1 = ops.relu(ops.lin(inp, 0))
+    rgb = torch.sigmoid(ops.lin(a1, 1))
+    return rgb, dict(inp=inp, a1=a1, rgb=rgb)
+
+
+def head_backward(ops, st, d_rgb):
+    inp, a1, rgb = st["inp"], st["a1"], st["rgb"]
+    dz1 = d_rgb * rgb * (1.0 - rgb)
+    dW1, db1 = ops.wgrad(dz1, a1), ops.colsum(dz1)
+    dz0 = ops.relu_bwd(ops.lin_t(dz1, 1), a1)
+    return ops.lin_t(dz0, 0), [ops.wgrad(dz0, inp), dW1], [ops.colsum(dz0), db1]
+

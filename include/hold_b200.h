@@ -224,6 +224,14 @@ int hold_shade(hold_ctx* ctx, int node, int R, int B, int S, const float* cam_lo
 int hold_composite(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors /*[n]*/,
                    const int32_t* class_ids_host /*[n]*/, const hold_render_out* comp,
                    const hold_render_out* per_node /*[n] or NULL*/, void* stream);
+
+/* Reverse mode of hold_composite (torch.autograd through merge_factors + density2weight + the integrals of volumetric_render in
+ * training, hold/hold_utils.py:76-121,243-271): upstream gradients of the composite render (g_comp) and / or of the n per-node
+ * renders (g_per_node[n]) -> gradients w.r.t. every node's color [R,S,3], normal [R,S,3] and density [R,S] (d_factors[k], overwritten;
+ * z_vals carry no gradient: the sampler runs under no_grad).  In a hold_render_out used as gradient any pointer may be NULL (= 0);
+ * fg_weights is ignored.  mask_prob's clamp(0, 1) passes the gradient where 0 <= sum(w) <= 1. */
+int hold_composite_bwd(hold_ctx* ctx, int n, int R, int S, const hold_factors* factors, const int32_t* class_ids_host,
+                       const hold_render_out* g_comp, const hold_render_out* g_per_node, const hold_factors* d_factors, void* stream);
 /* a18 (foreground): the whole path for n nodes, one call, no host sync. node_ids[k] are ctx node slots. */
 int hold_render_fg(hold_ctx* ctx, int n, const int32_t* node_ids_host, int R, int B, const float* cam_loc,
                    const float* ray_dirs, const hold_node_pose* poses /*[n]*/, const hold_factors* factors /*[n]*/,
@@ -260,6 +268,10 @@ int hold_rgb_eval(hold_ctx* ctx, int node, int B, int P, const float* x_c, const
  *    16..24  SDF W_l^T (A has N_l columns, C has K_l: 39 for l = 0)
  *    32..35  colour W_l, l = 0..3 (texture_net.py:95-100); l = 0 takes A in the order [feature (256) | x_c, n, pose (14) | time code (32)]
  *    48, 49  colour W_0^T: to the 256 feature inputs / to the other inputs [x_c, n, pose (14) | time code (32)];  50..52  colour W_1..3^T
+ * node = -1 addresses the background nets (model/renderables/background.py; packed by hold_bg_set_weights with HOLD_MLP_TC): 0..8 the
+ * implicit net's W_l (lin0: 116 inputs = PE-10 of the 4-d point (84) + frame code (32); lin3: 172 outputs, the skip re-feeds the 84 embedding columns), 16..24 their transposes, 32 the colour
+ * head's lin0 (315 -> 128, A in the order [feature (256) | view PE-4 (27), frame code (32)]), 48 / 49 its transpose to the features / to
+ * [view, frame code].
  * A and C rows must be 16-byte aligned (lda, ldc multiples of 4).  in_scale: device scalar (power of two) or NULL — A is fed as
  * A / in_scale and C multiplied back, which keeps small gradients inside the split's range. */
 int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda, int kvalid, int add_bias, const float* in_scale,
@@ -270,6 +282,9 @@ int hold_linear(hold_ctx* ctx, int node, int mat, int P, const float* A, int lda
  * two, NULL = 1) by which D / A are divided before the split; the result is multiplied back. */
 int hold_wgrad(hold_ctx* ctx, int P, const float* D, int ldd, int N, const float* A, int lda, int K, const float* d_scale,
                const float* a_scale, float* out, int ldo, void* stream);
+
+/* *scale_out (device) = 2^floor(log2(max |x|)) of the [P, ncols] matrix x (1e-30 floor): the operand scale hold_linear / hold_wgrad take. */
+int hold_pow2_scale(hold_ctx* ctx, int P, int ncols, const float* x, int ld, float* scale_out, void* stream);
 
 /* Pointwise steps of the training backward on [P, ld] fp32 matrices (hold_b200/csrc/train.cuh): op 0 ACT out0 = [softplus(z) | e],
  * out1 = softplus'(z); 1 MUL; 2 MULROW (in0 = one row); 3 U_DZ2 out0 = h s, out1 = h q softplus''(z); 4 DZ out0 = in0 in1 (+ in2);

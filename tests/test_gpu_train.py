@@ -53,6 +53,48 @@ def test_wgrad_kernel(ctx):
         assert e < 1e-5, f"P={P} N={N} K={K}: {e:.2e}"
 
 
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_composite_backward(ctx, n):
+    """hold_composite_bwd against float64 autograd through merge_factors + density2weight + the integrals (hold_utils.py:76-121,
+    243-271; the stable tie order of the kernels), with exact z ties between nodes, a ray whose mask saturates the clamp, and all
+    six outputs seeded."""
+    from hold_b200 import capi, train
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(10 + n)
+    R, S = 300, 26
+    cls = [2, 1, 3][:n]
+    fac64 = []
+    zshared = torch.sort(torch.rand(R, 6, generator=g) * 4.0, 1).values       # exact ties between the nodes
+    for k in range(n):
+        z = torch.sort(torch.cat([zshared, torch.rand(R, S - 6, generator=g) * 4.0], 1), 1).values
+        dens = torch.rand(R, S, generator=g) * 3.0
+        dens[0] = 50.0                                                        # opaque ray: sum of weights reaches 1 (clamp gate)
+        fac64.append(dict(color=torch.rand(R, S, 3, generator=g).double().requires_grad_(True), normal=torch.randn(R, S, 3, generator=g).double().requires_grad_(True),
+                          density=dens.double().requires_grad_(True), z_vals=z.double()))
+    sem = []
+    for k in range(n):
+        s_ = torch.zeros(R, S, 4, dtype=torch.float64)
+        s_[:, :, cls[k]] = 1.0
+        sem.append(s_)
+    ref = train.volumetric_render(train.merge_factors([dict(f, semantics=sem[k]) for k, f in enumerate(fac64)]))
+    seeds = {k: torch.randn(ref[k].shape, generator=g) for k in ("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights")}
+    sum((ref[k] * seeds[k].double()).sum() for k in seeds).backward()
+    fac = [dict(color=f["color"].detach().float().to(dev).requires_grad_(True), normal=f["normal"].detach().float().to(dev).requires_grad_(True),
+                density=f["density"].detach().float().to(dev).requires_grad_(True), z_vals=f["z_vals"].float().to(dev)) for f in fac64]
+    out = train.composite(ctx, fac, cls)
+    ctx.check()
+    for k in seeds:
+        assert rel(out[k], ref[k].reshape(out[k].shape)) < 1e-5, (k, rel(out[k], ref[k].reshape(out[k].shape)))
+    sum((out[k] * seeds[k].reshape(out[k].shape).to(dev)).sum() for k in seeds).backward()
+    ctx.check()
+    for k in range(n):
+        for name in ("color", "normal", "density"):
+            e = rel(fac[k][name].grad, fac64[k][name].grad)
+            print(f"composite n={n} node {k} d_{name}: {e:.2e}")
+            assert e < 1e-4, f"n={n} node {k} d_{name}: {e:.2e}"
+
+
 @pytest.mark.parametrize("nid", ["right", "object"])
 def test_sdf_net_function(env, ctx, nid):
     from hold_b200 import train
@@ -188,3 +230,91 @@ def test_node_training_forward_backward(env, ctx, nid):
         e = rel(got, want)
         print(f"{nid}: grad {name} {e:.2e}")
         assert e < 3e-4, f"{nid} grad {name}: {e:.2e}"
+
+
+def test_background_training(ctx):
+    """The NeRF++ background leg in training mode (hold_linear node -1 + hold_wgrad + hold_train_ew) against float64 autograd
+    over the oracle's `background` (which matches the reference's Background class, oracle/ref_harness.py check_background):
+    outputs and the gradients w.r.t. both background nets, the frame codes and the foreground's bg_weights."""
+    from hold_b200 import capi, scene_io, synth, train
+    from oracle import hold_oracle as O
+
+    sc = synth.make_scene(H=12, W=12, S=32, nodes=("right", "object"), B=2, seed=8)
+    sc.intrinsics[:, 0, 2] += 0.37
+    sc.intrinsics[:, 1, 2] -= 0.21
+    dev = torch.device("cuda", 0)
+    scene_io.build_net(sc, ctx, capi.MLP_TC)
+    bg, sdf_sd, rgb_sd = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+    dirs, cam = O.camera_rays(sc.uv, sc.extrinsics, sc.intrinsics)
+    P = dirs.shape[1]
+    dirs, cam = dirs.reshape(-1, 3), cam.unsqueeze(1).repeat(1, P, 1).reshape(-1, 3)
+    R = dirs.shape[0]
+    g = torch.Generator().manual_seed(3)
+    bgw = torch.rand(R, generator=g)
+    d_rgb, d_sem = torch.randn(R, 3, generator=g), torch.randn(R, 4, generator=g)
+    frame = torch.arange(sc.B).repeat_interleave(P)
+    idx = torch.as_tensor(sc.frame_idx)
+
+    # float64 oracle under autograd
+    emb = bg.frame_latent_encoder.weight.detach().cpu().double().requires_grad_(True)
+    s64 = {k: v.double().requires_grad_(True) for k, v in sdf_sd.items()}
+    r64 = {k: v.double().requires_grad_(True) for k, v in rgb_sd.items()}
+    bgw64 = bgw.double().requires_grad_(True)
+    o = O.background(bgw64, dirs.double(), cam.double(), emb[idx], frame, s64, r64, sc.bounding_sphere)
+    (o[0] * d_rgb.double()).sum().add((o[2] * d_sem.double()).sum()).backward()
+
+    # the kernels
+    bgw_d = bgw.to(dev).requires_grad_(True)
+    out = train.background_forward_train(bg, bgw_d, dirs.to(dev), cam.to(dev), idx.to(dev), sc.B, sc.bounding_sphere)
+    ctx.check()
+    for name, a, r in (("bg_rgb", out["bg_rgb"], o[0]), ("bg_rgb_only", out["bg_rgb_only"], o[1]), ("bg_semantics", out["bg_semantics"], o[2])):
+        err = (a.detach().cpu().double() - r.detach()).abs().max().item()
+        print(f"background: forward {name} {err:.2e}")
+        assert err <= 1e-4, f"{name}: {err:.2e}"
+    ((out["bg_rgb"] * d_rgb.to(dev)).sum() + (out["bg_semantics"] * d_sem.to(dev)).sum()).backward()
+    ctx.check()
+    checks = [("bg_weights", bgw_d.grad, bgw64.grad), ("frame codes", bg.frame_latent_encoder.weight.grad, emb.grad)]
+    for l in range(9):
+        lin = getattr(bg.bg_implicit_network, f"lin{l}")
+        checks += [(f"sdf.lin{l}.weight", lin.weight.grad, s64[f"lin{l}.weight"].grad), (f"sdf.lin{l}.bias", lin.bias.grad, s64[f"lin{l}.bias"].grad)]
+    for l in range(2):
+        lin = getattr(bg.bg_rendering_network, f"lin{l}")
+        checks += [(f"rgb.lin{l}.weight", lin.weight.grad, r64[f"lin{l}.weight"].grad), (f"rgb.lin{l}.bias", lin.bias.grad, r64[f"lin{l}.bias"].grad)]
+    for name, a, r in checks:
+        assert a is not None, f"no gradient for {name}"
+        e = rel(a.cpu().double(), r)
+        print(f"background: grad {name} {e:.2e}")
+        assert e <= 2e-4, f"grad {name}: rel {e:.2e}"
+
+
+def test_train_step_with_background(ctx):
+    """One optimiser step of the whole model (two nodes + background): every parameter that the loss reaches receives a finite
+    gradient, the loss is finite, and a second step at the same input lowers it (lr small enough for a descent step)."""
+    from hold_b200 import capi, scene_io, synth, train
+    from hold_b200.model import HOLDNet
+
+    sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), B=2, seed=5)
+    sc.intrinsics[:, 0, 2] += 0.37
+    dev = torch.device("cuda", 0)
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+    full = HOLDNet(ctx, dict(net.nodes), background=bg)
+    inp = scene_io.scene_input(sc, dev)
+    R = sc.B * sc.uv.shape[1]
+    g = torch.Generator(device=dev).manual_seed(0)
+    gt_rgb, gt_mask = torch.rand(R, 3, device=dev, generator=g), torch.zeros(R, 4, device=dev)
+    gt_mask[:, 0] = 1.0
+    ts = train.TrainStep(full, lr=1e-4, n_eik=64)
+    losses = []
+    for it in range(3):
+        loss, parts = ts.step(inp, gt_rgb, gt_mask, generator=torch.Generator(device=dev).manual_seed(1))
+        ctx.check()
+        assert torch.isfinite(loss).item(), parts
+        losses.append(loss.item())
+        if it == 0:
+            missing = [n for n, p in full.named_parameters() if p.requires_grad and (p.grad is None or not torch.isfinite(p.grad).all())]
+            assert not missing, f"parameters without a finite gradient: {missing[:8]}"
+            bg_grads = [p.grad.abs().max().item() for p in bg.parameters()]
+            assert max(bg_grads) > 0, "the background received no gradient"
+    print("train step losses", losses)
+    assert losses[-1] < losses[0], losses
