@@ -15,6 +15,7 @@ struct TcBg {
   float* rgb_w_last = nullptr;   // [3][256]: lin1 rows padded from 128 to 256 columns with zeros
   uint8_t* sdf_imgT[9] = {nullptr};   // training backward: W_l^T of the 9 layers (l = 8: the feature rows)
   uint8_t* rgb_imgT[2] = {nullptr};   // colour lin0^T: to the 256 feature inputs / to [view (27) | frame code (32)]
+  float* bias_s = nullptr;            // [10][256]: lin0..7 times kTcScaleA, lin8 (feature rows) plain, colour lin0 times kTcScaleA
 };
 
 __global__ void k_pad_rows(const float* __restrict__ src, int rows, int n_src, int n_dst, float* __restrict__ dst) {
@@ -28,7 +29,7 @@ static void tc_bg_free(TcBg*& t) {
   if (!t) return;
   for (int l = 0; l < 9; ++l) { cudaFree(t->sdf_img[l]); cudaFree(t->sdf_imgT[l]); }
   cudaFree(t->rgb_imgT[0]), cudaFree(t->rgb_imgT[1]);
-  cudaFree(t->rgb_img), cudaFree(t->rgb_w_last);
+  cudaFree(t->rgb_img), cudaFree(t->rgb_w_last), cudaFree(t->bias_s);
   delete t;
   t = nullptr;
 }
@@ -69,6 +70,11 @@ static int tc_bg_pack(hold_ctx* ctx, TcBg*& tp, const hold_mlp_weights* sdf, con
     k_tc_pack_T<<<256, 256, 0, s>>>(rgb->weight_v[0], nullptr, K0, 0, 128, K0, i == 0 ? 1 : 2, kBgView + kBgFrame, 1.0f, t.rgb_imgT[i]);
     HOLD_LAUNCH_CHECK(ctx);
   }
+  if (!t.bias_s) HOLD_CUDA(cudaMalloc((void**)&t.bias_s, 10 * 256 * sizeof(float)));
+  for (int l = 0; l < 10; ++l) {
+    k_scale_vec<<<1, 256, 0, s>>>(l < 9 ? ctx->bg_sdf.bias[l] : ctx->bg_rgb.bias[0], 256, l == 8 ? 1.0f : kTcScaleA, t.bias_s + 256 * l);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
   if (!t.rgb_w_last) HOLD_CUDA(cudaMalloc((void**)&t.rgb_w_last, 3 * 256 * sizeof(float)));
   k_pad_rows<<<3, 256, 0, s>>>(ctx->bg_rgb.w_last, 3, 128, 256, t.rgb_w_last);
   HOLD_LAUNCH_CHECK(ctx);
@@ -82,7 +88,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   memset(&a, 0, sizeof(a));
   a.P = P, a.n_layers = 9, a.pts_per_frame = P;
   for (int l = 0; l < 9; ++l) {
-    a.L[l].wimg = t.sdf_img[l], a.L[l].bias = ctx->bg_sdf.bias[l], a.L[l].nst = t.sdf_nst[l];
+    a.L[l].wimg = t.sdf_img[l], a.L[l].bias = t.bias_s + 256 * l, a.L[l].nst = t.sdf_nst[l];
     a.L[l].N = (l == 3) ? kHidden - kBgEmbed : kHidden;
   }
   a.w_last = ctx->bg_sdf.w_last, a.b_last = ctx->bg_sdf.b_last;
@@ -94,7 +100,7 @@ static int tc_bg_launch(hold_ctx* ctx, const TcBg& t, int P, const float* cam, c
   TcArgs c;
   memset(&c, 0, sizeof(c));
   c.P = P, c.n_layers = 1, c.pts_per_frame = P;
-  c.L[0].wimg = t.rgb_img, c.L[0].bias = ctx->bg_rgb.bias[0], c.L[0].nst = 10, c.L[0].N = 256;
+  c.L[0].wimg = t.rgb_img, c.L[0].bias = t.bias_s + 256 * 9, c.L[0].nst = 10, c.L[0].N = 256;
   c.w_last = t.rgb_w_last, c.b_last = ctx->bg_rgb.b_last;
   c.dirs = dirs, c.frame_code = frame_code, c.feat = feat, c.rgb = rgb, c.err = ctx->dev_err, c.unscale = kTcUnscale, c.passes = 3;
   c.k0 = kBgView + kBgFrame + kFeat;

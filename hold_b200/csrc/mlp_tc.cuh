@@ -16,6 +16,7 @@
 // rows) are fp32 dot products in the epilogue.  Gradients: reverse mode in the same kernel (MODE MLP_SDF_REV): the forward
 // epilogues stash softplus'(z_l) as unorm16 (512 KB per CTA: 76 MB for the grid, L2-resident; quantisation step 1.5e-5 moves
 // the gradient by <= 1.2e-5 of its scale, tests/test_cpu_stash_quant.py), the backward layers run over transposed weight images.
+// Embeddings (tile prologue, skip layer) are inlined branch-free sin/cos (sincos_cw).
 // Round-2 A/B on hardware (profiles/r02_variants.md) retired the other variants (base-2-domain epilogue, rebuilt 16-column
 // epilogue, CTA-pair kernels, forward-mode gradient): none beat this kernel at equal error.
 #pragma once
@@ -62,6 +63,7 @@ struct TcMlp {
   uint8_t* sdf_imgT[HOLD_MAX_LAYERS] = {nullptr};  // W_l^T images of layers 0..7 for the reverse-mode gradient, 8: feature rows (training)
   uint8_t* rgb_imgT[6] = {nullptr};                // training backward: [0] W_0^T feature part, [1] W_0^T other inputs, [2..4] W_1..3^T
   int sdf_nst[HOLD_MAX_LAYERS], rgb_nst[HOLD_MAX_LAYERS];
+  float* bias_s = nullptr;   // [13][256]: biases as the epilogues add them: SDF lin0..7 times kTcScaleA, lin8 (feature rows) plain, colour lin0..3 times kTcScaleA
 };
 
 struct TcArgs {
@@ -189,6 +191,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4;
 // kind::f16 instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, N=256, M=128
 constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescF16N64 = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // the same with N = 64
 
 // x = hi + lo: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
@@ -213,15 +216,16 @@ __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ft
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// kTcScaleA * Softplus(beta=100)(z) in its overflow-free form max(z,0) + log1p(exp(-|100 z|))/100 (two MUFU ops).
-// nn.Softplus' threshold branch (returns z for 100 z > 20) differs from this by < 2.1e-11.
-// u_out = exp(-|100 z|) for the derivative.
-__device__ __forceinline__ float softplus100_fast(float z, float& u_out) {
-  const float t = z * (100.0f * 1.4426950408889634f);
+// kTcScaleA * Softplus(beta=100)(z) in its overflow-free form max(z,0) + log1p(exp(-|100 z|))/100 (two MUFU ops), from
+// zs = kTcScaleA * z (the epilogue's bias FMA produces zs directly: accumulator scale and bias carry the power-of-two factor,
+// so every value is bit-identical to scaling afterwards).  nn.Softplus' threshold branch (returns z for 100 z > 20) differs
+// from this by < 2.1e-11.  u_out = exp(-|100 z|) for the derivative.
+__device__ __forceinline__ float softplus100_scaled(float zs, float& u_out) {
+  const float t = zs * (100.0f * 1.4426950408889634f / kTcScaleA);
   const float u = mufu_ex2(-fabsf(t));
   u_out = u;
   const float L = mufu_lg2(1.0f + u);
-  return fmaf(L, 0.6931471805599453f * 0.01f * kTcScaleA, fmaxf(z, 0.f) * kTcScaleA);
+  return fmaf(L, 0.6931471805599453f * 0.01f * kTcScaleA, fmaxf(zs, 0.f));
 }
 
 // unorm16 stash of softplus' in [0, 1]: encode by the magic-number add (round to nearest, no F2I), decode by OR-ing the
@@ -233,46 +237,88 @@ __device__ __forceinline__ uint32_t unorm16_pack2(float s0, float s1) {
 __device__ __forceinline__ float unorm16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8388608.0f; }
 __device__ __forceinline__ float unorm16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8388608.0f; }
 
-// One element of the Fourier embedding (engine/embedders.py:48-51) of a canonical point, or of its derivative
-// w.r.t. coordinate comp-1.  Deliberately NOT inlined: it is called from rolled loops at the tile prologue and
-// at the skip layer, and inlining 39 sinf/cosf bodies would blow the instruction cache of the hot epilogue.
-__device__ __noinline__ float embed_val(int e, int comp, float px, float py, float pz, const float* __restrict__ ew) {
-  if (e >= kEmbed) return 0.f;
-  const int d = e % 3;
-  const float pc = (d == 0) ? px : ((d == 1) ? py : pz);
-  float v;
-  if (e < 3) {
-    v = (comp == 0) ? pc : ((comp - 1 == d) ? 1.f : 0.f);
-  } else {
-    const int qq = (e - 3) / 3;
-    const float f = (float)(1 << (qq >> 1));
-    const float arg = pc * f;
-    if (comp == 0) v = (qq & 1) ? cosf(arg) : sinf(arg);
-    else v = (comp - 1 == d) ? ((qq & 1) ? -f * sinf(arg) : f * cosf(arg)) : 0.f;
-  }
-  if (ew != nullptr) v *= ew[e];
-  return v;
+// sin and cos of x for |x| < ~1e4 (the embeddings' arguments are coordinate * 2^k, k <= 9, |coordinate| <= a few): two-constant
+// Cody-Waite reduction by pi/2 with FMAs, Taylor kernels on [-pi/4, pi/4]; max abs error 7.1e-8 over the range used (libm's sinf:
+// 3.3e-8; the pin against the oracle's torch.sin is the stage tests' 1e-4).  No slow path, no calls: eight of these run
+// interleaved per epilogue hand-off.  (The libm sinf / cosf calls this replaces sat behind a non-inlined function and cost ~500
+// clocks EACH, serially, on the critical path of every tile's prologue and skip layer: 13 % of the sdf-only kernel.)
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+  const float k = rintf(x * 0.63661977236758134f);
+  float r = fmaf(k, -1.57079637050628662109375f, x);
+  r = fmaf(k, 4.371138828673793e-8f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, 2.7557319e-6f, -1.9841270e-4f);
+  sp = fmaf(sp, r2, 8.3333333e-3f);
+  sp = fmaf(sp, r2, -1.6666667e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, -2.7557319e-7f, 2.4801587e-5f);
+  cp = fmaf(cp, r2, -1.3888889e-3f);
+  cp = fmaf(cp, r2, 4.1666667e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const int q = __float2int_rn(k);
+  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
 }
 
-// Background nets (HOLD_BG_TC=1): element e of the 84-wide embedding of the 4-d inverted-sphere point (10 frequencies) and of the
-// 27-wide embedding of the view direction (4 frequencies), engine/embedders.py:48-51 layout.  Not inlined (rolled call sites).
-__device__ __noinline__ float bg_embed_val(int e, float p0, float p1, float p2, float p3) {
-  if (e >= kBgEmbed) return 0.f;
-  const int d = (e < 4) ? e : ((e - 4) & 3);
-  const float pc = (d == 0) ? p0 : ((d == 1) ? p1 : ((d == 2) ? p2 : p3));
-  if (e < 4) return pc;
-  const int qq = (e - 4) >> 2;
-  const float arg = pc * (float)(1 << (qq >> 1));
-  return (qq & 1) ? cosf(arg) : sinf(arg);
+// Eight consecutive elements e0 .. e0+7 of the Fourier embedding (engine/embedders.py:48-51: [x, sin(2^0 x), cos(2^0 x), sin(2^1 x),
+// ...], D coordinates per point, n_embed elements) or, DERIV, of its derivative w.r.t. the element's own coordinate.  Branch-free:
+// the eight sin/cos chains interleave (per-element branches serialise them: ~3 k clocks per hand-off on the tile's critical path).
+// ew: optional per-element weights (BarfEmbedder).  Returns the mask of elements that exist (0 <= e < n_embed); v[i] is finite
+// garbage elsewhere.
+template <int D, bool DERIV>
+__device__ __forceinline__ uint32_t embed8_inl(int e0, int n_embed, float x0, float x1, float x2, float x3, const float* __restrict__ ew,
+                                               float (&v)[8]) {
+  uint32_t okm = 0;
+  float w[8];
+  if (ew != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __ldg(ew + min(max(e0 + i, 0), n_embed - 1));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = e0 + i;
+    const bool ok = (unsigned)e < (unsigned)n_embed;
+    const int ec = ok ? e : 0;
+    const int g = (D == 4) ? (ec >> 2) : ((ec * 171) >> 9);   // ec / D (ec < 256)
+    const int d = ec - D * g;
+    const int qq = g - 1;                                     // -1: the identity block
+    const float pc = (d == 0) ? x0 : ((d == 1) ? x1 : ((d == 2 || D == 3) ? x2 : x3));
+    const float f = __int_as_float((127 + (max(qq, 0) >> 1)) << 23);
+    float sn, cs;
+    sincos_cw(pc * f, sn, cs);
+    float r = DERIV ? ((qq & 1) ? -f * sn : f * cs) : ((qq & 1) ? cs : sn);
+    r = (qq < 0) ? (DERIV ? 1.f : pc) : r;
+    v[i] = r * w[i];
+    okm |= ok ? (1u << i) : 0u;
+  }
+  return okm;
 }
-__device__ __noinline__ float view_embed_val(int e, float d0, float d1, float d2) {
-  if (e >= kBgView) return 0.f;
-  const int d = e % 3;
-  const float pc = (d == 0) ? d0 : ((d == 1) ? d1 : d2);
-  if (e < 3) return pc;
-  const int qq = (e - 3) / 3;
-  const float arg = pc * (float)(1 << (qq >> 1));
-  return (qq & 1) ? cosf(arg) : sinf(arg);
+
+// (Measured, profiles/r02_epilogue_experiments.md: making this and the head dot products out-of-line functions behind one
+// shared epilogue body -- to shrink the kernel from 49 KB to 28 KB of code -- was 5 % SLOWER than one specialised body per layer
+// kind with everything inlined: the branchy shared body costs more per hand-off than the instruction cache misses it avoids.)
+struct Embed8 { float v[8]; uint32_t ok; };
+template <int D, bool DERIV>
+__device__ __forceinline__ Embed8 embed8(int e0, int n_embed, float x0, float x1, float x2, float x3, const float* __restrict__ ew) {
+  Embed8 r;
+  if (e0 >= n_embed || e0 + 8 <= 0) {   // (warp-uniform) no element of this group exists
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    r.ok = 0;
+    return r;
+  }
+  r.ok = embed8_inl<D, DERIV>(e0, n_embed, x0, x1, x2, x3, ew, r.v);
+  return r;
+}
+// the 1- or 3-row output heads: fp32 dot products of 8 activation columns with the head rows
+__device__ __forceinline__ float head_dot8(const float* __restrict__ w, float o0, float o1, float o2, float o3, float o4, float o5, float o6, float o7) {
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+  return (o0 * w0.x + o1 * w0.y + o2 * w0.z + o3 * w0.w) + (o4 * w1.x + o5 * w1.y + o6 * w1.z + o7 * w1.w);
 }
 
 constexpr int kTcW = 4;                        // epilogue warps per TMEM lane quarter
@@ -291,7 +337,9 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // One arrival per epilogue WARP on the hand-off barrier: every lane orders its own st.shared against the async
 // proxy, the warp converges, lane 0 arrives.
 __device__ __forceinline__ void handoff_arrive(uint32_t bar, int lane) {
+#if !defined(HOLD_TC_EXP) || (HOLD_TC_EXP != 3 && HOLD_TC_EXP != 6)
   fence_proxy_async();
+#endif
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
@@ -307,8 +355,115 @@ struct TcCfg {
   static constexpr int kStages = kWide ? 2 : 3;
   static constexpr int kSmemA = 2 * kAChunks * kTcAChunkBytes;
   static constexpr int kSmemW = kStages * kTcStageBytes;
-  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 2, 8 B each) + 1 KB alignment slack
+  static constexpr int kSmemBytes = kSmemA + kSmemW + 256 + 1024;  // + barriers (<= 2*3 + 10 + 8, 8 B each) + 1 KB alignment slack
 };
+
+// Per-thread state of an epilogue warp (kept in registers: every user is force-inlined).
+struct EpiState {
+  uint32_t bAReady, bDFull, t_lane;
+  uint8_t* a_row;        // generic pointer to this thread's row inside A chunk 0 (hi part)
+  uint32_t u0, lo_off;   // byte offset of the thread's 16-byte unit for even hand-offs (odd: u0 ^ 64); hi -> lo part distance
+  int sub, lane, p;
+  bool valid;
+  float px, py, pz, pw;
+  float head0, head1, head2;
+  uint32_t d_par;        // bit b = parity to wait for on d_full[b]
+  volatile int* abort_flag;
+};
+
+// One layer of a forward chain (every mode but the reverse-mode gradient and hold_linear): wait for the accumulator, then 8
+// hand-offs of 32 columns; per hand-off this warp turns its 8 columns into the next layer's fp16 hi/lo operand.
+//   HEAD : the 1- (sdf) or 3-row (colour) output head is accumulated from this layer's activations (fp32 dot products)
+//   WRITE: the activations are the next MMA's operand (false on the chain's last MMA layer)
+//   FEAT : the layer's outputs are the 256-d feature vector (no activation, stored to global memory)
+//   SKIP : output columns >= a.L[l].N are the point's embedding (the skip connection into the next layer, shape_net.py:116-119)
+// One specialised body per layer kind (see the note at embed8).  a.L[l].bias is pre-multiplied by kTcScaleA unless FEAT
+// (TcMlp::bias_s).  The hand-off loop is unrolled by two with explicit ping-pong registers for the prefetched bias and
+// accumulator columns (a rotating prefetch costs 8 MOVs per hand-off).  The accumulator arrives in four 64-column quarters.
+template <int MODE, bool HEAD, bool WRITE, bool FEAT, bool SKIP>
+__device__ __forceinline__ bool epi_layer(const TcArgs& a, EpiState& E, const int l) {
+  constexpr bool kColorLike = (MODE == MLP_COLOR || MODE == MLP_BG_RGB);
+  const int N = a.L[l].N;
+  const float* bias = a.L[l].bias + E.sub * 8;
+  float4 nb[2][2];
+  nb[0][0] = __ldg(reinterpret_cast<const float4*>(bias));      // issued before the wait
+  nb[0][1] = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7
+  const bool rec = blockIdx.x == 0 && (E.p / kTcRows) == 2 * (int)gridDim.x && E.sub == 0 && (threadIdx.x & 127) == 64 && a.sig != nullptr;
+  uint32_t* rbuf = reinterpret_cast<uint32_t*>(a.sig) + l * 16;
+  if (rec) rbuf[0] = (uint32_t)clock();
+#endif
+  const uint32_t dbar = E.bDFull + 32 * (l & 1), dpar = (E.d_par >> (l & 1)) & 1;   // four quarter barriers, one parity (each completes once per layer)
+  if (!mbar_wait(dbar, dpar, a.err, 4, E.abort_flag)) return false;
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7
+  if (rec) rbuf[1] = (uint32_t)clock();
+#endif
+  E.d_par ^= (1u << (l & 1));
+  tc_fence_after();
+  const uint32_t t_col = E.t_lane + (uint32_t)((l & 1) * 256 + E.sub * 8);
+  const float us = FEAT ? a.unscale : a.unscale * kTcScaleA;
+  uint32_t raw[2][8];
+  tc_ld8(t_col, raw[0]);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int h = 2 * c + hb;
+      const int n0 = h * 32 + E.sub * 8;
+      if (hb == 0 || c < 3) {   // the next hand-off's bias: an un-prefetched load is a cache round trip on every hand-off's critical path
+        nb[hb ^ 1][0] = __ldg(reinterpret_cast<const float4*>(bias + 32 * (h + 1)));
+        nb[hb ^ 1][1] = __ldg(reinterpret_cast<const float4*>(bias + 32 * (h + 1)) + 1);
+      }
+      const float bv[8] = {nb[hb][0].x, nb[hb][0].y, nb[hb][0].z, nb[hb][0].w, nb[hb][1].x, nb[hb][1].y, nb[hb][1].z, nb[hb][1].w};
+      tc_wait_ld();
+      if (hb == 1 && c < 3) {   // the next hand-off opens the accumulator's next 64-column quarter
+        if (!mbar_wait(dbar + 8 * (c + 1), dpar, a.err, 4, E.abort_flag)) return false;
+        tc_fence_after();
+      }
+      if (hb == 0 || c < 3) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw[hb ^ 1]);   // prefetch the next hand-off's columns
+      float out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // accumulator -> pre-activation times kTcScaleA (undo the weight scaling, add the scaled bias); out[] is the next
+        // layer's operand, i.e. the activation times kTcScaleA (FEAT: the plain output)
+        const float zs = fmaf(__uint_as_float(raw[hb][i]), us, bv[i]);
+        float e;
+        out[i] = FEAT ? zs : (kColorLike ? fmaxf(zs, 0.f) : softplus100_scaled(zs, e));
+      }
+      if (SKIP && n0 + 8 > N) {  // skip connection: embedding columns of layer 3's output
+        const Embed8 ev = (MODE == MLP_BG_SDF) ? embed8<4, false>(n0 - N, kBgEmbed, E.px, E.py, E.pz, E.pw, nullptr)
+                                               : embed8<3, false>(n0 - N, kEmbed, E.px, E.py, E.pz, 0.f, a.embed_w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = (n0 + i >= N) ? (((ev.ok >> i) & 1u) ? kTcScaleA * ev.v[i] : 0.f) : out[i];
+      }
+      if (HEAD) {
+        E.head0 += head_dot8(a.w_last + n0, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+        if (kColorLike) {
+          E.head1 += head_dot8(a.w_last + 256 + n0, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+          E.head2 += head_dot8(a.w_last + 512 + n0, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+        }
+      }
+      if (FEAT) {
+        if (E.valid) {
+          float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)E.p * kFeat + n0);
+          dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+          dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+        }
+      } else if (WRITE) {
+        uint4 hi, lo;
+        split8(out, hi, lo);
+        uint8_t* dst = E.a_row + c * kTcAChunkBytes + (hb ? (E.u0 ^ 64u) : E.u0);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + E.lo_off) = lo;
+        handoff_arrive(E.bAReady + 16 * c + 8 * hb, E.lane);
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7
+        if (rec) rbuf[2 + h] = (uint32_t)clock();
+#endif
+      }
+    }
+  }
+  return true;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
@@ -323,7 +478,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   const uint32_t sA_hi = base, sA_lo = base + NA * kTcAChunkBytes, sW = base + Cfg::kSmemA;
   const uint32_t sBar = sW + Cfg::kSmemW;
   const uint32_t bWFull = sBar, bWEmpty = sBar + 8 * NS, bAReady = sBar + 16 * NS, bDFull = bAReady + 8 * NHO;
-  const uint32_t sTmemPtr = bDFull + 16, sAbort = bDFull + 20;
+  const uint32_t sTmemPtr = bDFull + 64, sAbort = bDFull + 68;   // d_full: [2 accumulators][4 column quarters]
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to `base`
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   volatile int* abort_flag = reinterpret_cast<volatile int*>(gen_base + (sAbort - base));
@@ -333,8 +488,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
     for (int i = 0; i < NS; ++i) { mbar_init(bWFull + 8 * i, 1); mbar_init(bWEmpty + 8 * i, 1); }
     *abort_flag = 0;
     for (int i = 0; i < NHO; ++i) mbar_init(bAReady + 8 * i, kTcEpiWarps);  // one arrival per epilogue warp
-    mbar_init(bDFull, 1);
-    mbar_init(bDFull + 8, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bDFull + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -382,27 +536,51 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             a_par ^= (1u << s);
             if (!__all_sync(0xffffffffu, mbar_wait(bWFull + 8 * stage, phase, a.err, 3, abort_flag))) goto tc_done;
             tc_fence_after();
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7   // cycle accounting (tools/exp_epilogue.py): stage s of layer l issued at
+            if (blockIdx.x == 0 && tile == 2 * (int)gridDim.x && lane == 0 && a.sig != nullptr) reinterpret_cast<uint32_t*>(a.sig)[256 + l * 16 + s] = (uint32_t)clock();
+#endif
             const uint32_t wb = sW + stage * kTcStageBytes;
             const bool el = elect_one();
+            if (s + 1 < nst) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
-              const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
-              const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
-              const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
-              const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
-              if (el) {
-                tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
-                if (a.passes >= 2) tc_mma(d_tmem, alo, whi, kIdescF16, 1);
-                if (a.passes >= 3) tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);  // bytes inside the 128-byte A row
+                const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+                const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+                const uint64_t whi = umma_desc(wb + j * 32, 512, kLayoutSW64);
+                const uint64_t wlo = umma_desc(wb + 16384 + j * 32, 512, kLayoutSW64);
+                if (el) {
+                  tc_mma(d_tmem, ahi, whi, kIdescF16, (s | j) != 0);
+                  if (a.passes >= 2) tc_mma(d_tmem, alo, whi, kIdescF16, 1);
+                  if (a.passes >= 3) tc_mma(d_tmem, ahi, wlo, kIdescF16, 1);
+                }
+              }
+            } else {
+              // the layer's LAST k stage goes out as four 64-column quarters, each committed on its own barrier: the epilogue
+              // starts on columns 0..63 while the other three quarters are still in the tensor pipe (measured: the accumulator-
+              // full signal sat ~1.1 k clocks after the last stage's issue, all of it tensor-pipe idle time of the next layer)
+#pragma unroll
+              for (int qn = 0; qn < 4; ++qn) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint32_t koff = (uint32_t)(((s & 1) * 2 + j) * 32);
+                  const uint64_t ahi = umma_desc(sA_hi + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+                  const uint64_t alo = umma_desc(sA_lo + c * kTcAChunkBytes + koff, 1024, kLayoutSW128);
+                  const uint64_t whi = umma_desc(wb + qn * 4096 + j * 32, 512, kLayoutSW64);          // rows 64 qn.. of the [256 n x 32 k] image
+                  const uint64_t wlo = umma_desc(wb + 16384 + qn * 4096 + j * 32, 512, kLayoutSW64);
+                  if (el) {
+                    tc_mma(d_tmem + (uint32_t)(64 * qn), ahi, whi, kIdescF16N64, (s | j) != 0);
+                    if (a.passes >= 2) tc_mma(d_tmem + (uint32_t)(64 * qn), alo, whi, kIdescF16N64, 1);
+                    if (a.passes >= 3) tc_mma(d_tmem + (uint32_t)(64 * qn), ahi, wlo, kIdescF16N64, 1);
+                  }
+                }
+                if (el) tc_commit(bDFull + 8 * ((l & 1) * 4 + qn));  // columns [64 qn, 64 qn + 64) of layer l's accumulator complete
               }
             }
             if (el) tc_commit(bWEmpty + 8 * stage);  // frees the weight stage when these MMAs have read it
             __syncwarp();
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
-          if (elect_one()) tc_commit(bDFull + 8 * (l & 1));  // accumulator of layer l complete
-          __syncwarp();
         }
       }
     }
@@ -460,12 +638,13 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         const int b = valid ? p / a.pts_per_frame : 0;
         for (int h = 0; h < 4; ++h) {
           float x[8];
+          const int e0 = h * 32 + sub * 8;
+          const Embed8 ev = embed8<4, false>(e0, kBgEmbed, px, py, pz, pw, nullptr);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int e = h * 32 + sub * 8 + i;
-            float v = 0.f;
-            if (e < kBgEmbed) v = bg_embed_val(e, px, py, pz, pw);
-            else if (e < kBgEmbed + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgEmbed];
+            const int e = e0 + i;
+            float v = ((ev.ok >> i) & 1u) ? ev.v[i] : 0.f;
+            if (e >= kBgEmbed && e < kBgEmbed + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgEmbed];
             x[i] = kTcScaleA * v;
           }
           uint4 hi, lo;
@@ -476,11 +655,15 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
           handoff_arrive(bAReady + 8 * h, lane);
         }
       } else if (!kColorLike) {
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7
+        if (blockIdx.x == 0 && tile == 2 * (int)gridDim.x && sub == 0 && (threadIdx.x & 127) == 64 && a.sig != nullptr) reinterpret_cast<uint32_t*>(a.sig)[12] = (uint32_t)clock();
+#endif
         if (valid) { px = a.xc[3 * (size_t)p], py = a.xc[3 * (size_t)p + 1], pz = a.xc[3 * (size_t)p + 2]; }
         for (int h = 0; h < 2; ++h) {
           float x[8];
+          const Embed8 ev = embed8<3, false>(h * 32 + sub * 8, kEmbed, px, py, pz, 0.f, a.embed_w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = kTcScaleA * embed_val(h * 32 + sub * 8 + i, 0, px, py, pz, a.embed_w);
+          for (int i = 0; i < 8; ++i) x[i] = ((ev.ok >> i) & 1u) ? kTcScaleA * ev.v[i] : 0.f;
           uint4 hi, lo;
           split8(x, hi, lo);
           const int j = h * 4 + sub;
@@ -503,15 +686,20 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               for (int i = 0; i < 8; ++i) x[i] = 0.f;
             }
           } else {
+            Embed8 ev;
+            ev.ok = 0;
+            if (MODE == MLP_BG_RGB) {
+              const int ray = valid ? p / kBgN : 0;
+              ev = embed8<3, false>(k0 - kFeat, kBgView, a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2], 0.f, nullptr);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int e = k0 + i - kFeat;  // [x_c(3), n(3), pose_embed(8), time_code(32)]; background: [view PE-4 (27), frame code (32)]
               float v = 0.f;
               if (MODE == MLP_BG_RGB) {
                 if (valid) {
-                  const int ray = p / kBgN;
-                  if (e < kBgView) v = view_embed_val(e, a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2]);
-                  else if (e < kBgView + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgView];
+                  if ((ev.ok >> i) & 1u) v = ev.v[i];
+                  else if (e >= kBgView && e < kBgView + kBgFrame) v = a.frame_code[b * kBgFrame + e - kBgView];
                 }
               } else if (valid) {
                 if (e < 3) v = a.xc[3 * (size_t)p + e];
@@ -538,7 +726,7 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         // ======== one layer: C = acc * unscale (* in_scale) + bias, fp32 rows of [P, ldc], columns [0, nvalid) ========
         const float* bias = a.L[0].bias;
         const float osc = (a.in_scale != nullptr) ? a.unscale * __ldg(a.in_scale) : a.unscale;
-        if (!mbar_wait(bDFull, d_par & 1, a.err, 4, abort_flag)) break;
+        if (!mbar_wait(bDFull + 24, d_par & 1, a.err, 4, abort_flag)) break;   // the last column quarter: the whole accumulator is complete
         d_par ^= 1u;
         tc_fence_after();
         const uint32_t t_col = t_lane + (uint32_t)(sub * 8);
@@ -580,7 +768,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         // only (.cg): 512 KB per CTA.  Reads run two hand-offs ahead of their use (an L2 round trip is ~1 hand-off long).
         uint16_t* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
         constexpr float kInvQ = 1.0f / 65535.0f;
-        for (int st = 0; st < 17; ++st) {
+        bool rev_ok = true;
+        for (int st = 0; st < 17 && rev_ok; ++st) {
           const int kind = (st < 8) ? 0 : ((st == 8) ? 1 : ((st < 16) ? 2 : 3));
           const int l = (st <= 8) ? st : 16 - st;
           const float* bias = (kind <= 1) ? a.L[st].bias : nullptr;
@@ -596,7 +785,8 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             sq0 = __ldcg(reinterpret_cast<const uint4*>(srow + sub * 8));
             sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + 32 + sub * 8));
           }
-          if (!mbar_wait(bDFull + 8 * (st & 1), (d_par >> (st & 1)) & 1, a.err, 4, abort_flag)) break;
+          const uint32_t dbar = bDFull + 32 * (st & 1), dpar = (d_par >> (st & 1)) & 1;
+          if (!mbar_wait(dbar, dpar, a.err, 4, abort_flag)) break;
           d_par ^= (1u << (st & 1));
           tc_fence_after();
           const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 8);
@@ -615,8 +805,13 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
             if (srow != nullptr && h + 2 < 8) sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + n0 + 64));
             tc_wait_ld();
             float acc[8];
+            const float us = (kind == 0) ? a.unscale * kTcScaleA : a.unscale;   // forward layers work on kTcScaleA * z (bias pre-scaled)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * a.unscale;
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * us;
+            if ((h & 1) && h + 1 < 8) {   // the next hand-off opens the accumulator's next 64-column quarter
+              if (!mbar_wait(dbar + 8 * ((h + 1) >> 1), dpar, a.err, 4, abort_flag)) { rev_ok = false; break; }
+              tc_fence_after();
+            }
             if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
             float out[8];
             if (kind == 0) {
@@ -625,16 +820,16 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
               for (int i = 0; i < 8; ++i) {
                 float e;
                 const float z = acc[i] + bv[i];
-                out[i] = softplus100_fast(z, e);
+                out[i] = softplus100_scaled(z, e);
                 const float r = mufu_rcp(1.0f + e);
                 sg[i] = (z >= 0.f) ? r : e * r;
               }
               __stcg(reinterpret_cast<uint4*>(sig + (size_t)l * (kTcRows * 256) + n0),
                      make_uint4(unorm16_pack2(sg[0], sg[1]), unorm16_pack2(sg[2], sg[3]), unorm16_pack2(sg[4], sg[5]), unorm16_pack2(sg[6], sg[7])));
               if (l == 3 && n0 + 8 > 217) {
+                const Embed8 ev = embed8<3, false>(n0 - 217, kEmbed, px, py, pz, 0.f, a.embed_w);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (n0 + i >= 217) out[i] = kTcScaleA * embed_val(n0 + i - 217, 0, px, py, pz, a.embed_w);
+                for (int i = 0; i < 8; ++i) out[i] = ((ev.ok >> i) & 1u) ? kTcScaleA * ev.v[i] : out[i];
               }
               if (l == 7) {
 #pragma unroll
@@ -663,30 +858,28 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * acc[i] * sv[i];
                 if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
+                  const Embed8 dv = embed8<3, true>(n0 - 217, kEmbed, px, py, pz, 0.f, a.embed_w);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    if (n0 + i >= 217) {
-                      const int e = n0 + i - 217, d = e % 3;
-                      const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
-                      head1 += (d == 0) ? je : 0.f;
-                      head2 += (d == 1) ? je : 0.f;
-                      gz_acc += (d == 2) ? je : 0.f;
-                      out[i] = 0.f;
-                    }
+                    const int ec = max(n0 + i - 217, 0), d = ec - 3 * ((ec * 171) >> 9);
+                    const bool ok = (dv.ok >> i) & 1u;
+                    const float je = ok ? acc[i] * dv.v[i] : 0.f;
+                    head1 += (d == 0) ? je : 0.f;
+                    head2 += (d == 1) ? je : 0.f;
+                    gz_acc += (d == 2) ? je : 0.f;
+                    out[i] = ok ? 0.f : out[i];
                   }
                 }
               } else {  // kind 3: d sdf / d embed through layer 0's input
                 if (n0 < 40) {
+                  const Embed8 dv = embed8<3, true>(n0, kEmbed, px, py, pz, 0.f, a.embed_w);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    const int e = n0 + i;
-                    if (e < kEmbed) {
-                      const int d = e % 3;
-                      const float je = acc[i] * embed_val(e, d + 1, px, py, pz, a.embed_w);
-                      head1 += (d == 0) ? je : 0.f;
-                      head2 += (d == 1) ? je : 0.f;
-                      gz_acc += (d == 2) ? je : 0.f;
-                    }
+                    const int e = n0 + i, d = e - 3 * ((e * 171) >> 9);
+                    const float je = ((dv.ok >> i) & 1u) ? acc[i] * dv.v[i] : 0.f;
+                    head1 += (d == 0) ? je : 0.f;
+                    head2 += (d == 1) ? je : 0.f;
+                    gz_acc += (d == 2) ? je : 0.f;
                   }
                 }
               }
@@ -723,87 +916,26 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         epi_bar();
         continue;
       }
-      for (int l = 0; l < a.n_layers; ++l) {
-        const bool feat_layer = (MODE == MLP_BG_SDF) && (l == a.n_layers - 1);
-        const bool head_layer = kColorLike ? (l == a.n_layers - 1) : (l == 7);
-        const bool last_mma = (l == a.n_layers - 1);
-        const int N = a.L[l].N;
-        const float* bias = a.L[l].bias;
-        float4 nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));      // issued before the wait
-        float4 nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
-        if (!mbar_wait(bDFull + 8 * (l & 1), (d_par >> (l & 1)) & 1, a.err, 4, abort_flag)) break;
-        d_par ^= (1u << (l & 1));
-        tc_fence_after();
-        const uint32_t t_col = t_lane + (uint32_t)((l & 1) * 256 + sub * 8);
-        uint32_t raw[8];
-        tc_ld8(t_col, raw);
-#pragma unroll 2
-        for (int h = 0; h < 8; ++h) {
-          const int n0 = h * 32 + sub * 8;
-          // bias of this hand-off was requested one hand-off earlier (L1 is ~0 KB at this smem carve-out: an
-          // un-prefetched __ldg is an L2 round trip on the critical path of every hand-off)
-          const float4 b0 = nb0, b1 = nb1;
-          if (h + 1 < 8) {
-            nb0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32));
-            nb1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32) + 1);
-          }
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          tc_wait_ld();
-          float acc[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]);
-          if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);  // prefetch the next hand-off's columns
-          float out[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // accumulator -> pre-activation (undo the operand scaling, add the bias); out[] holds the next layer's
-            // operand, i.e. the activation times kTcScaleA (the feature layer's output is unscaled)
-            const float z = fmaf(acc[i], a.unscale, bv[i]);
-            float o;
-            if (kColorLike) {
-              o = fmaxf(z, 0.f) * kTcScaleA;
-            } else if (feat_layer) {
-              o = z;
-            } else {
-              float e = 0.f;
-              o = softplus100_fast(z, e);
-            }
-            out[i] = o;
-          }
-          if (!kColorLike && n0 + 8 > N) {  // skip connection: embedding columns of layer 3's output
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (n0 + i >= N)
-                out[i] = kTcScaleA * ((MODE == MLP_BG_SDF) ? bg_embed_val(n0 + i - N, px, py, pz, pw) : embed_val(n0 + i - N, 0, px, py, pz, a.embed_w));
-          }
-          if (head_layer) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
-              head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
-              if (kColorLike) {
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + 256 + n0) + i);
-                const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.w_last + 512 + n0) + i);
-                head1 += out[4 * i] * w1.x + out[4 * i + 1] * w1.y + out[4 * i + 2] * w1.z + out[4 * i + 3] * w1.w;
-                head2 += out[4 * i] * w2.x + out[4 * i + 1] * w2.y + out[4 * i + 2] * w2.z + out[4 * i + 3] * w2.w;
-              }
-            }
-          }
-          if (feat_layer) {
-            if (valid) {
-              float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
-              dst[0] = make_float4(out[0], out[1], out[2], out[3]);
-              dst[1] = make_float4(out[4], out[5], out[6], out[7]);
-            }
-          } else if (!last_mma) {
-            uint4 hi, lo;
-            split8(out, hi, lo);
-            const int c = h >> 1, j = (h & 1) * 4 + sub;
-            *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
-            *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-            handoff_arrive(bAReady + 8 * h, lane);
-          }
+      {
+        EpiState E;
+        E.bAReady = bAReady, E.bDFull = bDFull, E.t_lane = t_lane;
+        E.a_row = gA_hi + (row >> 3) * 1024 + (row & 7) * 128;
+        E.u0 = (uint32_t)((sub ^ (row & 7)) << 4), E.lo_off = (uint32_t)(NA * kTcAChunkBytes);
+        E.sub = sub, E.lane = lane, E.p = p, E.valid = valid;
+        E.px = px, E.py = py, E.pz = pz, E.pw = pw;
+        E.head0 = 0.f, E.head1 = 0.f, E.head2 = 0.f, E.d_par = d_par, E.abort_flag = abort_flag;
+        bool ok = true;
+        for (int l = 0; l < a.n_layers && ok; ++l) {
+          const bool head_layer = kColorLike ? (l == a.n_layers - 1) : (l == 7);
+          const bool last_mma = (l == a.n_layers - 1);
+          if (MODE == MLP_BG_SDF && last_mma) ok = epi_layer<MODE, false, false, true, false>(a, E, l);           // the feature rows
+          else if (MODE == MLP_BG_SDF && head_layer) ok = epi_layer<MODE, true, true, false, false>(a, E, l);
+          else if (head_layer) ok = epi_layer<MODE, true, false, false, false>(a, E, l);
+          else if (!kColorLike && l == 3) ok = epi_layer<MODE, false, true, false, true>(a, E, l);
+          else ok = epi_layer<MODE, false, true, false, false>(a, E, l);
         }
+        d_par = E.d_par, head0 = E.head0, head1 = E.head1, head2 = E.head2;
+        if (!ok) break;
       }
       // ---------------------------------------------------------- heads: fixed-order reduction over the quarter's warps
       // (all MMAs of the tile have completed, so the A region is free to hold the partial sums)
@@ -939,6 +1071,7 @@ static void tc_free(NodeState& ns) {
     if (ns.tc->sdf_imgT[l]) cudaFree(ns.tc->sdf_imgT[l]);
     if (l < 6 && ns.tc->rgb_imgT[l]) cudaFree(ns.tc->rgb_imgT[l]);
   }
+  if (ns.tc->bias_s) cudaFree(ns.tc->bias_s);
   delete ns.tc;
   ns.tc = nullptr;
 }
@@ -970,6 +1103,11 @@ static int tc_pack(hold_ctx* ctx, NodeState& ns, const hold_mlp_weights* sdf, co
                                     t.rgb_imgT[i]);
     HOLD_LAUNCH_CHECK(ctx);
   }
+  if (!t.bias_s) HOLD_CUDA(cudaMalloc((void**)&t.bias_s, 13 * 256 * sizeof(float)));
+  for (int l = 0; l < 13; ++l) {   // (the fp32 packing of this call has already written ns.sdf.bias / ns.rgb.bias on this stream)
+    k_scale_vec<<<1, 256, 0, s>>>(l < 9 ? ns.sdf.bias[l] : ns.rgb.bias[l - 9], 256, l == 8 ? 1.0f : kTcScaleA, t.bias_s + 256 * l);
+    HOLD_LAUNCH_CHECK(ctx);
+  }
   for (int l = 0; l < 4; ++l) {
     const int K = (l == 0) ? rgb->in_dim[0] : 256, kpad = (l == 0) ? 320 : 256;
     t.rgb_nst[l] = kpad / 32;
@@ -989,13 +1127,16 @@ static int tc_launch_sdf(hold_ctx* ctx, NodeState& ns, int P, const float* xc, c
   memset(&a, 0, sizeof(a));
   a.P = P, a.n_layers = rev ? 17 : 8;
   for (int l = 0; l < 9; ++l) {
-    a.L[l].wimg = ns.tc->sdf_img[l], a.L[l].bias = ns.sdf.bias[l], a.L[l].nst = ns.tc->sdf_nst[l], a.L[l].N = ns.sdf.N[l];
+    a.L[l].wimg = ns.tc->sdf_img[l], a.L[l].bias = ns.tc->bias_s + 256 * l, a.L[l].nst = ns.tc->sdf_nst[l], a.L[l].N = ns.sdf.N[l];
   }
   a.w_last = ns.sdf.w_last, a.b_last = ns.sdf.b_last;
   a.xc = xc, a.embed_w = embed_w, a.sdf = sdf, a.grad = grad, a.feat = feat, a.st = st, a.err = ctx->dev_err;
   a.passes = (st != nullptr && ctx->sampler_passes >= 1 && ctx->sampler_passes <= 3) ? ctx->sampler_passes : 3;
   a.unscale = kTcUnscale * (1.0f + (float)(ctx->tc_acc_comp >= 0 ? ctx->tc_acc_comp : kTcAccComp) * (1.0f / 16777216.0f));
   const int tiles = ceil_div(P, kTcRows), grid = min(tiles, ctx->sm_count);
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 7
+  if (!rev) { void* rb = nullptr; if (ws_get(ctx, 12, 4096, &rb)) return HOLD_E_CUDA; a.sig = (uint16_t*)rb; }
+#endif
   if (rev) {
     HOLD_REQUIRE(grad != nullptr && feat != nullptr, "sdf eval with gradient needs both grad and feat buffers");
     void* sig = nullptr;
@@ -1036,7 +1177,7 @@ static int tc_launch_rgb(hold_ctx* ctx, NodeState& ns, int P, int pts_per_frame,
   memset(&a, 0, sizeof(a));
   a.P = P, a.n_layers = 4;
   for (int l = 0; l < 4; ++l) {
-    a.L[l].wimg = ns.tc->rgb_img[l], a.L[l].bias = ns.rgb.bias[l], a.L[l].nst = ns.tc->rgb_nst[l], a.L[l].N = 256;
+    a.L[l].wimg = ns.tc->rgb_img[l], a.L[l].bias = ns.tc->bias_s + 256 * (9 + l), a.L[l].nst = ns.tc->rgb_nst[l], a.L[l].N = 256;
   }
   a.w_last = ns.rgb.w_last, a.b_last = ns.rgb.b_last;
   a.xc = xc, a.normal = normal, a.pose_embed = pe, a.feat = const_cast<float*>(feat), a.time_code = time_code;
