@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -4
-timeout 900 python bench.py --no-extras 2>gpurun_out/r2y_bench.err | tee gpurun_out/r2y_bench.json | cut -c1-300
+for n in 101 0 7 101 0; do timeout 300 python tools/exp_epilogue.py --run $n 2>&1 | grep "^exp\|^  layer\|^  tile"; done | tee gpurun_out/r3a_exp_epilogue.log
+timeout 1200 python -m pytest tests/test_gpu_tc.py tests/test_gpu_stages.py tests/test_gpu_e2e.py tests/test_gpu_sampler_rounds.py tests/test_gpu_edges.py -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -4
