@@ -558,14 +558,208 @@ def composite(ctx, factors, class_ids):
     return dict(zip(("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights"), outs))
 
 
+# ------------------------------------------------------------------------------------------------ training-mode forward (hold_net.py:53-134)
+SEGM_IDS = {"bg": 0, "object": 50, "right": 150, "left": 250}     # utils/const.py:1
+
+
+class PointInSpace:
+    """hold/hold_utils.py:22-56: one point near each centre + a share of uniform samples in a box."""
+
+    def __init__(self, global_sigma=0.5, global_sigma_xyz=None, local_sigma=0.01):
+        self.global_sigma_xyz = torch.ones(3) * global_sigma if global_sigma_xyz is None else torch.as_tensor(global_sigma_xyz, dtype=torch.float32)
+        self.local_sigma = local_sigma
+
+    def get_points(self, pc_input, local_sigma=None, global_ratio=0.125, generator=None):
+        B, N, D = pc_input.shape
+        dev = pc_input.device
+        sig = self.global_sigma_xyz.to(dev)
+        ls = self.local_sigma if local_sigma is None else local_sigma
+        local = pc_input + torch.randn(pc_input.shape, device=dev, generator=generator) * ls
+        glob = torch.rand(B, int(N * global_ratio), D, device=dev, generator=generator) * (sig * 2) - sig
+        return torch.cat([local, glob], 1)
+
+
+pt_in_space_sampler_h = PointInSpace(global_sigma_xyz=[0.15, 0.06, 0.12])     # hold_utils.py:58
+
+
+def sample_on_barycentric_mesh(verts, faces, num_samples, generator=None):
+    """hold/hold_utils.py:272-304."""
+    B = verts.shape[0]
+    dev = verts.device
+    fi = torch.randint(0, faces.shape[0], (B, num_samples), device=dev, generator=generator)
+    sf = faces.long()[fi]
+    v0, v1, v2 = (torch.gather(verts, 1, sf[..., k].unsqueeze(-1).expand(-1, -1, 3)) for k in range(3))
+    u, v = torch.rand(B, num_samples, 1, device=dev, generator=generator), torch.rand(B, num_samples, 1, device=dev, generator=generator)
+    m = u + v > 1
+    u, v = torch.where(m, 1 - u, u), torch.where(m, 1 - v, v)
+    return u * v0 + v * v1 + (1 - u - v) * v2
+
+
+def compute_gradient_samples(sampler, node, num_pixels, verts_c, B, local_sigma=0.008, global_ratio=0.20, generator=None):
+    """engine/volsdf_utils.py:19-48: grad_theta = d sdf / d x at samples around the canonical vertices (local branch) or uniform in
+    [-0.3, 0.3]^3 (verts_c None); differentiable w.r.t. the SDF net (the second-order path of SdfNetFn)."""
+    dev = node.density.beta.device
+    if verts_c is not None:
+        idx = torch.randperm(verts_c.shape[1], device=dev, generator=generator)[:num_pixels]
+        sample = sampler.get_points(verts_c.index_select(1, idx), local_sigma=local_sigma, global_ratio=global_ratio, generator=generator)
+    else:
+        sample = torch.rand(B, num_pixels, 3, device=dev, generator=generator) * 0.6 - 0.3
+    Ws, bs = _folded_sdf(node)
+    _, _, g = SdfNetFn.apply(node, sample.reshape(-1, 3).contiguous(), *Ws, *bs)
+    return g.reshape(sample.shape)
+
+
+def prepare_loss_targets(out, node, B, P, canonical_pts, generator=None):
+    """prepare_loss_targets_hand / _object (hold/hold_utils.py:149-241): <node>.index_off_surface, <node>.grad_theta and, for hands,
+    <node>.pts2mano_sdf_cano / <node>.pred_sdf.  The canonical meshes are attributes the caller sets, as the reference does
+    (mano_node.py:112-134 `mesh_v_cano_div`, `mesh_f_cano_div`; object_node.py:112-132 `mesh_vo_cano`, `mesh_fo_cano`); without them the
+    reference skips the node's targets, and so does this."""
+    from . import ops
+
+    nid, ctx = node.node_id, node.ctx
+    Ws, bs = _folded_sdf(node)
+    if node.kind == "hand":
+        if getattr(node, "mesh_v_cano_div", None) is None:
+            return
+        v = node.mesh_v_cano_div[None].repeat(B, 1, 1).float().contiguous()
+        f = node.mesh_f_cano_div
+        samples = pt_in_space_sampler_h.get_points(sample_on_barycentric_mesh(v, f, 256, generator), local_sigma=0.008, global_ratio=0.20, generator=generator)
+        with torch.no_grad():
+            out[f"{nid}.pts2mano_sdf_cano"] = ops.compute_mano_cano_sdf(ctx, v, f, samples.contiguous())
+            off, _ = ops.check_off_in_surface_points_cano_mesh(ctx, v, f, canonical_pts.detach().reshape(B, -1, 3).contiguous(), B * P, threshold=0.01)
+        sdf, _, _ = SdfNetFn.apply(node, samples.reshape(-1, 3).contiguous(), *Ws, *bs)            # query_oc (hold_utils.py:61-65)
+        out[f"{nid}.pred_sdf"] = sdf.reshape(B, -1)
+        out[f"{nid}.index_off_surface"] = off
+        verts_c = node.server.verts_c.expand(B, -1, -1)
+        out[f"{nid}.grad_theta"] = compute_gradient_samples(pt_in_space_sampler_h, node, 256, verts_c, B, 0.008, 0.20, generator)
+    else:
+        if getattr(node, "mesh_vo_cano", None) is None:
+            return
+        v = node.mesh_vo_cano.reshape(1, -1, 3).repeat(B, 1, 1).float().contiguous()
+        with torch.no_grad():
+            off, _ = ops.check_off_in_surface_points_cano_mesh(ctx, v, node.mesh_fo_cano, canonical_pts.detach().reshape(B, -1, 3).contiguous(), B * P, threshold=0.05)
+        out[f"{nid}.index_off_surface"] = off
+        xyz = v[0].abs().max(0).values * 1.1
+        out[f"{nid}.grad_theta"] = compute_gradient_samples(PointInSpace(global_sigma_xyz=xyz.cpu()), node, 256, v, B, 0.03, 0.20, generator)
+
+
+def forward_train(net, input, generator=None):
+    """HOLDNet.forward in training mode (hold/hold_net.py:53-134) -> the reference's output dict: epoch, step, fg_rgb, fg_weights-free
+    composite keys (mask_prob, normal, depth, fg_semantics, bg_weights), <node>.* of every node's own volumetric_render, the loss
+    targets of prepare_loss_targets, bg_z_vals, ray_dirs, cam_loc, index, and (forward) rgb, semantics, bg_rgb_only.
+    Every floating-point output carries the autograd graph to the nets, beta, poses / transforms and codes.  Training-mode rules
+    mirrored: pose conditioning is zeroed while current_epoch < 20 (mano_node.py:82-85); sampling runs without gradients
+    (ray_sampler.py, torch.no_grad)."""
+    from . import ops
+    from .model import ErrorBoundSampler
+
+    uv = input["uv"]
+    B, P, _ = uv.shape
+    dev = uv.device
+    out = {}
+    if "current_epoch" in input:
+        out["epoch"], out["step"] = input["current_epoch"], input.get("global_step", 0)
+    early = int(input.get("current_epoch", 1 << 30)) < 20
+    dirs, cam = ops.camera_rays(net.ctx, uv, input["extrinsics"], input["intrinsics"])
+    fr = torch.arange(B, device=dev).repeat_interleave(P)
+    factors = []
+    for node in net.nodes.values():
+        node.sync_weights()
+        pose, keep, srv, tfs = node.articulate(input)     # servers under autograd when the pose rows require grad
+        with torch.no_grad():
+            z, _ = ErrorBoundSampler(node).get_z_vals(dirs, cam, pose, B)
+        S = z.shape[1]
+        x = (cam[:, None, :] + z[:, :, None] * dirs[:, None, :]).reshape(B, P * S, 3)
+        hand = node.kind == "hand"
+        pc = None
+        if hand:
+            pc = input[f"{node.node_id}.full_pose"][:, 3:] / math.pi
+            if early:
+                pc = pc * 0.0
+        o = node_forward_train(node, x, srv["tfs"] if hand else tfs, srv["verts"] if hand else None, fr.repeat_interleave(S),
+                               pose_cond=pc, time_code=None if hand else node.frame_latent_encoder(input["idx"]), sync=False)
+        f = dict(color=o["color"].reshape(B * P, S, 3), normal=o["normal"].reshape(B * P, S, 3), density=o["density"].reshape(B * P, S), z_vals=z)
+        factors.append(f)
+        prepare_loss_targets(out, node, B, P, o["x_c"], generator)
+        own = composite(net.ctx, [f], [node.class_id])                      # volumetric_render(myfactors) (hold_net.py:86-88)
+        for k, v in own.items():
+            out[f"{node.node_id}.{k}"] = v
+    comp = composite(net.ctx, factors, [nd.class_id for nd in net.nodes.values()])
+    out.update(comp)
+    R_s = next(iter(net.nodes.values())).bounding_sphere
+    out["bg_z_vals"] = (torch.linspace(0.0, 1.0, 32, device=dev) * (1.0 / R_s))[None].expand(B * P, 32)
+    out["ray_dirs"], out["cam_loc"], out["index"] = dirs, cam, input["idx"]
+    rgb, sem = comp["fg_rgb"], comp["fg_semantics"]
+    if getattr(net, "background", None) is not None:                        # hold_net.py:110-134
+        bgo = background_forward_train(net.background, comp["bg_weights"], dirs, cam, input["idx"], B, R_s)
+        rgb, sem = rgb + bgo["bg_rgb"], sem + bgo["bg_semantics"]
+        out["bg_rgb_only"] = bgo["bg_rgb_only"]
+    out["rgb"], out["semantics"] = rgb, sem
+    return out
+
+
+class Loss(torch.nn.Module):
+    """hold/loss.py:9-96 with hold/loss_terms.py: L1 rgb, L2 semantics against the one-hot segmentation, opacity sparseness off the
+    surface, eikonal (kept only above its lower bound), clamped L1 between the SDF net and the MANO canonical mesh; the reference's
+    weights and schedules."""
+
+    def __init__(self, milestone=30000):
+        super().__init__()
+        self.milestone = milestone
+
+    def forward(self, batch, mo):
+        rgb_gt = batch["gt.rgb"].reshape(-1, 3)
+        mask_gt = batch["gt.mask"].reshape(-1)
+        B = batch["idx"].shape[0]
+        scores = torch.ones(B, device=rgb_gt.device)
+        valid = torch.ones_like(mask_gt, dtype=torch.float32)
+        per_px = lambda n: scores[:, None].repeat(1, n // B).reshape(-1, 1)
+        ok = ~torch.any(mo["rgb"].isnan(), dim=1)
+        l = (mo["rgb"][ok] - rgb_gt[ok]).abs() * valid[ok][:, None]
+        rgb_loss = (l * per_px(l.shape[0])).sum() / (valid[ok].sum() + 1e-6)
+        sem = mask_gt.clone().float()                                                # loss_terms.py:70-97
+        cls = torch.zeros_like(sem, dtype=torch.long)
+        cls[(sem >= 25) & (sem < 100)] = 1
+        cls[(sem >= 100) & (sem < 200)] = 2
+        cls[sem >= 200] = 3
+        onehot = torch.nn.functional.one_hot(cls, len(SEGM_IDS)).float()
+        sl = (mo["semantics"] - onehot) ** 2 * valid[:, None]
+        sem_loss = (sl * per_px(sl.shape[0])).sum() / valid.sum()
+        sparse = 0.0
+        for k in [k for k in mo if k.endswith(".index_off_surface")]:
+            nid = k.split(".")[0]
+            acc, off = mo[f"{nid}.mask_prob"].reshape(-1, 1), mo[k]
+            sparse = sparse + (acc[off].abs() * per_px(acc.shape[0])[off]).mean()
+        eik = 0.0
+        for k in [k for k in mo if k.endswith("grad_theta")]:
+            eik = eik + ((mo[k].norm(2, dim=-1) - 1) ** 2).mean()
+        mano = 0.0
+        for k in [k for k in mo if k.endswith("pts2mano_sdf_cano")]:
+            nid = k.split(".")[0]
+            p, g = torch.clamp(mo[f"{nid}.pred_sdf"], -0.01, 0.01), torch.clamp(mo[k].detach(), -0.01, 0.01)
+            mano = mano + ((p - g).abs() * scores[:, None]).mean()
+        progress = min(self.milestone, int(mo.get("step", 0)))
+        w_sem = torch.linspace(1.1, 0.1, self.milestone + 1)[progress]
+        w_sparse = torch.linspace(0.0, 1.0, self.milestone + 1)[progress]
+        d = {"loss/rgb": rgb_loss * 1.0, "loss/sem": sem_loss * w_sem}
+        eik = eik * 0.00001
+        if float(eik.detach() if torch.is_tensor(eik) else eik) > 0.0008:
+            d["loss/eikonal"] = eik
+        d["loss/mano_cano"] = mano * 5.0
+        d["loss/opacity_sparse"] = sparse * w_sparse
+        d["loss"] = sum(d[k] for k in list(d))
+        return d
+
+
 class TrainStep:
     """One data-parallel training step of the foreground model (hold/hold.py:110-137 without the Lightning plumbing): every
     rank takes its share of the step's rays, runs sampler (no grad) -> nodes in training mode -> merge + integrate -> losses,
     back-propagates through the kernels above, then ONE all-reduce over a single flat gradient bucket (shard.allreduce_grads_,
     the only collective of the step: SURVEY §8e) and the optimiser step (Adam, hold.py:79-101).
-    Losses here: L1 rgb, L2 semantics (loss_terms.py:14-21, :60-70) and the eikonal term on uniform canonical samples
-    (volsdf_utils.py:19-48, global branch; loss.py:83-87).  The kaolin-based terms (mano_cano, opacity_sparse) need the
-    canonical meshes; their targets are served by hold_mesh_sdf / hold_off_in_surface (ops.py) and are added by the caller."""
+    The forward is `forward_train` (the reference's training-mode output dict).  Losses of this benchmark step: L1 rgb, L2 semantics
+    (loss_terms.py:14-21, :60-70) and the eikonal term (volsdf_utils.py:19-48; loss.py:83-87); the full reference loss incl. the
+    kaolin-target terms (mano_cano, opacity_sparse) is `Loss` (pinned to the reference's module, tests/test_cpu_loss.py) on the
+    same output dict once the canonical meshes are attached to the nodes."""
 
     def __init__(self, net, lr=1e-4, n_eik=256, group=None):
         self.net, self.group, self.n_eik = net, group, n_eik
@@ -573,40 +767,13 @@ class TrainStep:
         self.opt = torch.optim.Adam(self.params, lr=lr)
 
     def forward_loss(self, input, gt_rgb, gt_mask, generator=None):
-        from . import ops
-        from .model import ErrorBoundSampler
-
-        net = self.net
-        uv = input["uv"]
-        B, P, _ = uv.shape
-        dev = uv.device
-        dirs, cam = ops.camera_rays(net.ctx, uv, input["extrinsics"], input["intrinsics"])
-        fr = torch.arange(B, device=dev).repeat_interleave(P)
-        factors, eik = [], []
-        for node in net.nodes.values():
-            node.sync_weights()
-            pose, keep, srv, tfs = node.articulate(input)     # servers under autograd when the pose rows require grad
-            with torch.no_grad():
-                z, _ = ErrorBoundSampler(node).get_z_vals(dirs, cam, pose, B)   # eval-mode sampling: training randomness via `rand`
-            S = z.shape[1]
-            x = (cam[:, None, :] + z[:, :, None] * dirs[:, None, :]).reshape(B, P * S, 3)
-            frp = fr.repeat_interleave(S)
-            hand = node.kind == "hand"
-            o = node_forward_train(node, x, srv["tfs"] if hand else tfs, srv["verts"] if hand else None, frp,
-                                   pose_cond=(input[f"{node.node_id}.full_pose"][:, 3:] / math.pi) if hand else None,
-                                   time_code=None if hand else node.frame_latent_encoder(input["idx"]), sync=False)
-            factors.append(dict(color=o["color"].reshape(B * P, S, 3), normal=o["normal"].reshape(B * P, S, 3),
-                                density=o["density"].reshape(B * P, S), z_vals=z))
-            # eikonal samples: uniform in [-0.3, 0.3]^3 (volsdf_utils.py:38-42), gradient through the same function
-            xs = (torch.rand(B * self.n_eik, 3, device=dev, generator=generator) * 0.6 - 0.3)
-            Ws, bs = _folded_sdf(node)
-            _, _, ge = SdfNetFn.apply(node, xs, *Ws, *bs)
-            eik.append(((ge.norm(2, dim=-1) - 1) ** 2).mean())
-        comp = composite(net.ctx, factors, [nd.class_id for nd in net.nodes.values()])     # hold_composite / hold_composite_bwd
-        rgb, sem = comp["fg_rgb"], comp["fg_semantics"]
-        if getattr(net, "background", None) is not None:                                    # hold_net.py:110-134: rgb = fg + bg_weights * bg
-            bgo = background_forward_train(net.background, comp["bg_weights"], dirs, cam, input["idx"], B, next(iter(net.nodes.values())).bounding_sphere)
-            rgb, sem = rgb + bgo["bg_rgb"], sem + bgo["bg_semantics"]
+        out = forward_train(self.net, input, generator)
+        B = input["uv"].shape[0]
+        eik = [((out[k].norm(2, dim=-1) - 1) ** 2).mean() for k in out if k.endswith("grad_theta")]
+        if not eik:   # no canonical meshes attached to the nodes: the global branch (volsdf_utils.py:36-43), uniform in [-0.3, 0.3]^3
+            eik = [((compute_gradient_samples(None, node, self.n_eik, None, B, generator=generator).norm(2, dim=-1) - 1) ** 2).mean()
+                   for node in self.net.nodes.values()]
+        rgb, sem = out["rgb"], out["semantics"]
         valid = gt_rgb.shape[0]
         loss_rgb = (rgb - gt_rgb).abs().sum() / (valid + 1e-6)
         loss_sem = ((sem - gt_mask) ** 2).mean()

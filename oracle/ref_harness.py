@@ -391,6 +391,43 @@ def golden_background():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def _loss_case(seed, step, with_targets):
+    """A synthetic training output dict + batch for hold/loss.py (the keys HOLDNet.forward writes in training mode)."""
+    g = torch.Generator().manual_seed(seed)
+    B, P = 2, 24
+    R = B * P
+    r = lambda *sh: torch.rand(*sh, generator=g)
+    mo = {"rgb": r(R, 3), "semantics": r(R, 4), "step": step, "epoch": 3}
+    mask = torch.tensor([0, 50, 150, 250, 24, 99, 101, 201])[torch.randint(0, 8, (R,), generator=g)]
+    batch = {"idx": torch.arange(B), "gt.rgb": r(B, P, 3), "gt.mask": mask.reshape(B, P), "im_path": [["unused"]]}
+    for nid in ("right", "object"):
+        mo[f"{nid}.mask_prob"] = r(R, 1)
+        if with_targets:
+            mo[f"{nid}.index_off_surface"] = r(R) > 0.6
+            mo[f"{nid}.grad_theta"] = torch.randn(B, 307, 3, generator=g) * (12.0 if nid == "right" else 1.0)
+    if with_targets:
+        mo["right.pts2mano_sdf_cano"] = torch.randn(B, 307, generator=g) * 0.02
+        mo["right.pred_sdf"] = torch.randn(B, 307, generator=g) * 0.02
+    return batch, mo
+
+
+def golden_loss():
+    """tests/golden/loss/*.pt: synthetic training outputs + the loss dict of the REFERENCE's hold/loss.py Loss module."""
+    from src.hold.loss import Loss
+    from common.xdict import xdict
+
+    d = os.path.join(REPO, "tests", "golden", "loss")
+    os.makedirs(d, exist_ok=True)
+    for name, (seed, step, wt) in {"early_no_targets": (1, 0, False), "mid_targets": (2, 12000, True), "late_targets": (3, 45000, True)}.items():
+        batch, mo = _loss_case(seed, step, wt)
+        L = Loss(ns())
+        L.im_w, L.im_h = 64, 64            # skips the PIL read of the frame's image file
+        ld = L(batch, xdict(mo))
+        path = os.path.join(d, name + ".pt")
+        torch.save({"batch": batch, "outputs": mo, "loss": {k: torch.as_tensor(v).detach().clone() for k, v in ld.items()}}, path)
+        print("wrote", path, {k: float(v) for k, v in ld.items()})
+
+
 def golden():
     """tests/golden/*.pt: inputs are regenerated from the seed; outputs come from the REFERENCE modules."""
     from hold_b200 import synth
@@ -435,3 +472,5 @@ if __name__ == "__main__":
         golden()
     elif cmd == "golden_background":
         golden_background()
+    elif cmd == "golden_loss":
+        golden_loss()

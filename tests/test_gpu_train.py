@@ -318,3 +318,73 @@ def test_train_step_with_background(ctx):
             assert max(bg_grads) > 0, "the background received no gradient"
     print("train step losses", losses)
     assert losses[-1] < losses[0], losses
+
+
+def _hull_faces(pts):
+    from scipy.spatial import ConvexHull
+
+    return torch.as_tensor(ConvexHull(pts.detach().cpu().double().numpy()).simplices.astype("int32"))
+
+
+def test_forward_train_outputs_and_loss(ctx):
+    """forward_train = HOLDNet.forward in training mode (hold_net.py:53-134): the reference's output keys, the epoch < 20 rule of
+    mano_node.py:82-85, agreement of its composite with the eval-mode render (same samples), and the full reference loss
+    (train.Loss, pinned to hold/loss.py by tests/test_cpu_loss.py) back-propagating into every net."""
+    from hold_b200 import capi, scene_io, synth, train
+    from hold_b200.model import HOLDNet
+
+    sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), B=2, seed=11)
+    sc.intrinsics[:, 0, 2] += 0.37
+    dev = torch.device("cuda", 0)
+    net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+    full = HOLDNet(ctx, dict(net.nodes), background=bg)
+    right, obj = full.nodes["right"], full.nodes["object"]
+    right.mesh_v_cano_div = right.server.verts_c[0].detach().clone()
+    right.mesh_f_cano_div = _hull_faces(right.mesh_v_cano_div).to(dev)
+    obj.mesh_vo_cano = sc.obj_pts_cano.to(dev)
+    obj.mesh_fo_cano = _hull_faces(sc.obj_pts_cano).to(dev)
+    inp = scene_io.scene_input(sc, dev)
+    B, P = inp["uv"].shape[:2]
+    R = B * P
+    g = torch.Generator(device=dev).manual_seed(0)
+    late = train.forward_train(full, {**inp, "current_epoch": 30, "global_step": 12000}, generator=g)
+    ctx.check()
+    want = {"epoch", "step", "fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights", "bg_z_vals", "ray_dirs", "cam_loc", "index",
+            "rgb", "semantics", "bg_rgb_only", "right.pts2mano_sdf_cano", "right.pred_sdf"}
+    for nid in ("right", "object"):
+        want |= {f"{nid}.{k}" for k in ("fg_rgb", "mask_prob", "normal", "depth", "fg_semantics", "bg_weights", "index_off_surface", "grad_theta")}
+    assert want <= set(late), sorted(want - set(late))
+    assert late["right.index_off_surface"].shape == (R,) and late["right.index_off_surface"].dtype == torch.bool
+    assert late["right.grad_theta"].shape == (B, 307, 3) and late["object.grad_theta"].shape == (B, 307, 3)
+    assert late["right.pts2mano_sdf_cano"].shape == (B, 307) and late["right.pred_sdf"].shape == (B, 307)
+    # same samples, same weights: the training forward (hold_linear chains) reproduces the eval render (fused chains)
+    with torch.no_grad():
+        ev = full(inp)
+    for k in ("rgb", "fg_rgb", "mask_prob", "depth"):
+        d = (late[k].detach().reshape(-1) - ev[k].reshape(-1)).abs().max().item()
+        print(f"forward_train vs eval render, {k}: {d:.2e}")
+        assert d <= 2e-4, (k, d)
+    # epoch < 20: the colour net's pose conditioning is zeroed -> only the hand's colour moves
+    early = train.forward_train(full, {**inp, "current_epoch": 3, "global_step": 100}, generator=g)
+    assert (early["right.fg_rgb"] - late["right.fg_rgb"]).abs().max().item() > 1e-5
+    assert (early["object.fg_rgb"] - late["object.fg_rgb"]).abs().max().item() <= 1e-6
+    assert (early["right.depth"] - late["right.depth"]).abs().max().item() <= 1e-6
+    # the reference loss on the training outputs, back-propagated
+    gt = torch.Generator(device=dev).manual_seed(1)
+    batch = {"idx": inp["idx"], "gt.rgb": torch.rand(B, P, 3, device=dev, generator=gt),
+             "gt.mask": torch.tensor([0, 50, 150], device=dev)[torch.randint(0, 3, (B, P), device=dev, generator=gt)]}
+    full.zero_grad(set_to_none=True)
+    ld = train.Loss()(batch, late)
+    assert {"loss/rgb", "loss/sem", "loss/mano_cano", "loss/opacity_sparse", "loss"} <= set(ld)
+    assert all(torch.isfinite(torch.as_tensor(v)).item() for v in ld.values()), ld
+    ld["loss"].backward()
+    ctx.check()
+    for name, p in full.named_parameters():
+        if "object.rendering_network.lin_pose" in name:
+            continue   # unused by the reference too: an object has no pose parameters (texture_net.py:80-87)
+        if p.requires_grad and p.numel() > 0 and (".implicit_network." in name or ".rendering_network." in name or name.startswith("background.bg_")):
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert right.implicit_network.lin4.weight_v.grad.abs().max().item() > 0
+    assert bg.bg_implicit_network.lin2.weight.grad.abs().max().item() > 0
+    print({k: float(v) for k, v in ld.items()})

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-for n in 101 0 7 101 0; do timeout 300 python tools/exp_epilogue.py --run $n 2>&1 | grep "^exp\|^  layer\|^  tile"; done | tee gpurun_out/r3a_exp_epilogue.log
-timeout 1200 python -m pytest tests/test_gpu_tc.py tests/test_gpu_stages.py tests/test_gpu_e2e.py tests/test_gpu_sampler_rounds.py tests/test_gpu_edges.py -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -4
+timeout 900 python -m pytest tests/test_gpu_train.py -q -s -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" > gpurun_out/r3c_train.log; grep -n "forward_train\|passed\|failed\|FAILED\|Error\|error\|losses\|loss/" gpurun_out/r3c_train.log | head -40; tail -30 gpurun_out/r3c_train.log | grep -v "^tests/"
