@@ -112,3 +112,43 @@ def test_rendering_network_call(env, ctx):
             ref = O.rgb_mlp(pts, nrm, None, fv, sc.rgb_state[nid])
         ctx.check()
         assert rel(out, ref) < 1e-4, f"{nid}: {rel(out, ref):.2e}"
+
+
+def test_constructors_from_reference_config(ctx):
+    """dropin.HOLDNet(opt, betas_r, betas_l, num_frames, args) built from the `model:` block of confs/general.yaml renders the same
+    pixels as the mirror assembled by hand (same weights), and the per-node objects are hold_b200.model.Node instances."""
+    import copy
+
+    from hold_b200 import capi, dropin, scene_io, synth
+
+    sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), B=2, seed=4)
+    sc.intrinsics[:, 0, 2] += 0.37
+    dev = torch.device("cuda", 0)
+    opt = copy.deepcopy(dropin._SUPPORTED)
+    opt["rendering_network"]["d_in"] = 14
+    opt["density"] = {"params_init": {"beta": 0.1}, "beta_min": 1e-4}
+    opt["ray_sampler"] = dict(sc.sampler, N_samples_inverse_sphere=32)
+    opt["scene_bounding_sphere"] = sc.bounding_sphere
+    args = {"n_images": sc.B, "case": "synthetic"}
+    net = dropin.HOLDNet(opt, sc.betas["right"], None, sc.B, args, ctx=ctx, mano_r=sc.mano["right"], obj_pts=sc.obj_pts_cano, mlp_mode=capi.MLP_TC).to(dev)
+    assert list(net.nodes) == ["right", "object"] and net.background is not None
+    assert opt["rendering_network"]["d_in"] == 14 + 32     # the reference's in-place edit (object_node.py:19)
+    ref = scene_io.build_net(sc, ctx, capi.MLP_TC)
+    ref_sd = {nid: {k: v.clone() for k, v in ref.nodes[nid].state_dict().items()} for nid in ref.nodes}
+    for nid, node in net.nodes.items():
+        node.load_state_dict(ref_sd[nid], strict=True)
+        node.sync_weights()
+    bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+    bg_sd = {k: v.clone() for k, v in bg.state_dict().items()}
+    inp = scene_io.scene_input(sc, dev)
+    net.background.load_state_dict(bg_sd, strict=True)
+    net.background.sync_weights()
+    a = net(inp)
+    from hold_b200.model import HOLDNet
+    for node in ref.nodes.values():   # the two nets share ctx slots: re-upload the hand-assembled one's weights before using it
+        node.sync_weights()
+    bg.sync_weights()
+    b = HOLDNet(ctx, dict(ref.nodes), background=bg)(inp)
+    ctx.check()
+    for k in ("rgb", "fg_rgb", "depth", "normal", "semantics"):
+        assert torch.equal(a[k], b[k]), k
