@@ -515,7 +515,6 @@ int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, con
   if (rnd) { a.jitter = rnd->jitter, a.u_rand = rnd->u, a.extra_idx = rnd->extra_idx; }
   a.z_out = z_vals, a.iters_out = iters;
   const int wpb = 4;
-  const int samp_smem = wpb * 6 * kMaxZ * (int)sizeof(float);
   k_sampler_init<<<ceil_div(R, wpb), wpb * 32, 0, s>>>(a);
   HOLD_LAUNCH_CHECK(ctx);
   for (int it = 0; it < c.max_total_iters; ++it) {
@@ -528,9 +527,11 @@ int hold_sample(hold_ctx* ctx, int node, int R, int B, const float* cam_loc, con
     if (rc) return rc;
     rc = launch_sdf(ctx, ns, R * Ne, xc, pose->embed_w, sdfnew, nullptr, nullptr, ns.sstate, s);
     if (rc) return rc;
-    k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+    const int cap = sampler_cap(it, Ne, c.n_samples + c.n_samples_extra + 2);
+    const int samp_smem = wpb * 6 * cap * (int)sizeof(float);
+    k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it, cap);
     HOLD_LAUNCH_CHECK(ctx);
-    k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+    k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it, cap);
     HOLD_LAUNCH_CHECK(ctx);
   }
   return HOLD_OK;
@@ -580,13 +581,14 @@ int hold_sampler_round(hold_ctx* ctx, int node, int R, int it, const float* z_ol
   a.z = zb, a.sdf = sb, a.znew = znew, a.sdfnew = sdfnew, a.beta = betab, a.far = farb, a.st = ns.sstate, a.err = ctx->dev_err;
   a.z_out = zfin, a.iters_out = nullptr;
   const int wpb = 4;
-  const int samp_smem = wpb * 6 * kMaxZ * (int)sizeof(float);
-  k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+  const int cap = sampler_cap(it, Ne, c.n_samples + c.n_samples_extra + 2);
+  const int samp_smem = wpb * 6 * cap * (int)sizeof(float);
+  k_sampler_merge_beta<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it, cap);
   HOLD_LAUNCH_CHECK(ctx);
   if (z_merged) HOLD_CUDA(cudaMemcpy2DAsync(z_merged, n * sizeof(float), zb, kMaxZ * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
   if (sdf_merged) HOLD_CUDA(cudaMemcpy2DAsync(sdf_merged, n * sizeof(float), sb, kMaxZ * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToDevice, s));
   HOLD_CUDA(cudaMemcpyAsync(beta_out, betab, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it);
+  k_sampler_resample<<<ceil_div(R, wpb), wpb * 32, samp_smem, s>>>(a, it, cap);
   HOLD_LAUNCH_CHECK(ctx);
   // upsample decision of this round (ray_sampler.py:244-246), read back for the caller: it sizes samples_out
   unsigned int bits = 0;

@@ -170,11 +170,24 @@ struct RaySmem {
   float* t1;
 };
 
-__device__ __forceinline__ RaySmem ray_smem(float* base, int warp_in_block) {
+// `cap` = elements per array for THIS launch (sampler_cap(): round `it` holds (it + 1) n_eval samples, not kMaxZ): six arrays of kMaxZ
+// floats per ray allowed 3 blocks = 12 warps per SM (ncu: 18 % of the warp slots, `wait` / short-scoreboard stalls unhidden).
+__device__ __forceinline__ RaySmem ray_smem(float* base, int warp_in_block, int cap) {
   RaySmem m;
-  float* p = base + (size_t)warp_in_block * 6 * kMaxZ;
-  m.z = p, m.s = p + kMaxZ, m.dstar = p + 2 * kMaxZ, m.delta = p + 3 * kMaxZ, m.t0 = p + 4 * kMaxZ, m.t1 = p + 5 * kMaxZ;
+  float* p = base + (size_t)warp_in_block * 6 * cap;
+  m.z = p, m.s = p + cap, m.dstar = p + 2 * cap, m.delta = p + 3 * cap, m.t0 = p + 4 * cap, m.t1 = p + 5 * cap;
   return m;
+}
+// capacity the two round kernels need at round `it`: the merged buffer, the power-of-two padded new samples (bitonic sort) and the
+// power-of-two padded final set
+static inline int sampler_cap(int it, int n_eval, int n_final) {
+  int np2 = 1, sp2 = 1;
+  while (np2 < n_eval) np2 <<= 1;
+  while (sp2 < n_final) sp2 <<= 1;
+  int cap = (it + 1) * n_eval;
+  if (cap < np2) cap = np2;
+  if (cap < sp2) cap = sp2;
+  return (cap + 31) & ~31;
 }
 
 // Theorem-1 bound d* per interval (ray_sampler.py:191-206)
@@ -227,13 +240,13 @@ __device__ __forceinline__ float error_bound(const RaySmem& m, int n, float beta
 
 // Round part A: merge the round's new (z, sdf) into the sorted buffers, d*, beta line search (:179-220),
 // contribute to the batch-global max.
-__global__ void __launch_bounds__(128) k_sampler_merge_beta(SamplerArgs a, int it) {
+__global__ void __launch_bounds__(128) k_sampler_merge_beta(SamplerArgs a, int it, int cap) {
   if (a.st->done) return;
   extern __shared__ float smem[];
   const int wib = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int r = blockIdx.x * (blockDim.x / 32) + wib;
   if (r >= a.R) return;
-  RaySmem m = ray_smem(smem, wib);
+  RaySmem m = ray_smem(smem, wib, cap);
   const int Ne = a.n_eval, n_old = it * Ne, n = n_old + Ne;
   // new samples -> t0/t1 (sorted by z; the inverse-CDF output is monotone up to rounding, sort keeps
   // torch.sort's multiset semantics); Ne is padded to a power of two with +inf
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(128) k_sampler_merge_beta(SamplerArgs a, int i
 
 // Round part B: opacity / error-bound PDF -> inverse-CDF samples (:223-307); either the next round's Ne new
 // samples or the final set (N from the weight CDF + near + far + strided extras, sorted; :313-336).
-__global__ void __launch_bounds__(128) k_sampler_resample(SamplerArgs a, int it) {
+__global__ void __launch_bounds__(128) k_sampler_resample(SamplerArgs a, int it, int cap) {
   if (a.st->done) return;
   extern __shared__ float smem[];
   const int wib = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(128) k_sampler_resample(SamplerArgs a, int it)
     if (a.iters_out != nullptr) a.iters_out[0] = it + 1;
   }
   if (r >= a.R) return;
-  RaySmem m = ray_smem(smem, wib);
+  RaySmem m = ray_smem(smem, wib, cap);
   const int Ne = a.n_eval, n = (it + 1) * Ne;
   for (int k = lane; k < n; k += 32) {
     m.z[k] = a.z[(size_t)r * kMaxZ + k];
