@@ -465,6 +465,142 @@ __device__ __forceinline__ bool epi_layer(const TcArgs& a, EpiState& E, const in
   return true;
 }
 
+// Reverse-mode chain (MODE MLP_SDF_REV), one step = one accumulator: d sdf/d z_7 = w_sdf * s_7;  d sdf/d z_{l-1} = (g_l . W_l) * s_{l-1};
+// the embedding columns (skip input of layer 4, input of layer 0) collect d sdf/d embed, chained with d embed/d x_c per column.
+//   KIND 0: forward layer l = st (stashes s_l = softplus'(z_l));  SPEC 1: l = 3 (skip columns), SPEC 2: l = 7 (sdf head)
+//   KIND 1: the feature layer (st = 8): writes the 256-d feature, seeds g_7 = w_sdf * s_7
+//   KIND 2: backward layer l = 16 - st: operand of the next step = acc * s_{l-1};  SPEC 1: l = 4 (its columns >= 217 are d sdf/d embed)
+//   KIND 3: st = 16: d sdf / d embed through layer 0's input, no operand
+// One specialised body per (KIND, SPEC), same structure as epi_layer (ping-pong registers for the prefetched bias / accumulator
+// columns; the stash words are read two hand-offs ahead into the slot that was just consumed).  The monolithic step body this
+// replaces issued 223 instructions per 8-column hand-off (ncu) against 107 in the forward-only chain.
+// Stash: s_l as unorm16, written and later read by the SAME thread (row, 8 columns per hand-off), L2 only (.cg): 512 KB per CTA.
+struct RevState {
+  uint16_t* sig;         // this thread's row of the CTA's stash, [8 layers][128 rows][256]
+  float gz;              // d sdf / d z (head1 / head2 of the EpiState hold d/dx, d/dy)
+};
+
+template <int KIND, int SPEC>
+__device__ __forceinline__ bool rev_step(const TcArgs& a, EpiState& E, RevState& R, const int st) {
+  constexpr float kInvQ = 1.0f / 65535.0f;
+  constexpr int kRowStride = kTcRows * 256;
+  const int l = (st <= 8) ? st : 16 - st;
+  const float* bias = (KIND <= 1) ? a.L[st].bias + E.sub * 8 : nullptr;
+  // stash row read by this step: s_7 for the feature layer's seed, s_{l-1} for backward layer l
+  const uint16_t* srow = (KIND == 1) ? R.sig + (size_t)7 * kRowStride + E.sub * 8 : ((KIND == 2) ? R.sig + (size_t)(l - 1) * kRowStride + E.sub * 8 : nullptr);
+  float4 nb[2][2];
+  uint4 sq[2];
+  if (KIND <= 1) {
+    nb[0][0] = __ldg(reinterpret_cast<const float4*>(bias));
+    nb[0][1] = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+  }
+  if (KIND == 1 || KIND == 2) {
+    sq[0] = __ldcg(reinterpret_cast<const uint4*>(srow));
+    sq[1] = __ldcg(reinterpret_cast<const uint4*>(srow + 32));
+  }
+  const uint32_t dbar = E.bDFull + 32 * (st & 1), dpar = (E.d_par >> (st & 1)) & 1;
+  if (!mbar_wait(dbar, dpar, a.err, 4, E.abort_flag)) return false;
+  E.d_par ^= (1u << (st & 1));
+  tc_fence_after();
+  const uint32_t t_col = E.t_lane + (uint32_t)((st & 1) * 256 + E.sub * 8);
+  const float us = (KIND == 0) ? a.unscale * kTcScaleA : a.unscale;   // forward layers work on kTcScaleA * z (bias pre-scaled)
+  uint32_t raw[2][8];
+  tc_ld8(t_col, raw[0]);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int h = 2 * c + hb;
+      const int n0 = h * 32 + E.sub * 8;
+      if (KIND <= 1 && (hb == 0 || c < 3)) {
+        nb[hb ^ 1][0] = __ldg(reinterpret_cast<const float4*>(bias + 32 * (h + 1)));
+        nb[hb ^ 1][1] = __ldg(reinterpret_cast<const float4*>(bias + 32 * (h + 1)) + 1);
+      }
+      const float bv[8] = {nb[hb][0].x, nb[hb][0].y, nb[hb][0].z, nb[hb][0].w, nb[hb][1].x, nb[hb][1].y, nb[hb][1].z, nb[hb][1].w};
+      const uint4 sqv = sq[hb];
+      if ((KIND == 1 || KIND == 2) && c < 3) sq[hb] = __ldcg(reinterpret_cast<const uint4*>(srow + 32 * (h + 2)));   // two hand-offs ahead
+      tc_wait_ld();
+      if (hb == 1 && c < 3) {   // the next hand-off opens the accumulator's next 64-column quarter
+        if (!mbar_wait(dbar + 8 * (c + 1), dpar, a.err, 4, E.abort_flag)) return false;
+        tc_fence_after();
+      }
+      if (hb == 0 || c < 3) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw[hb ^ 1]);
+      float out[8];
+      if (KIND == 0) {
+        float sg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float e;
+          const float zs = fmaf(__uint_as_float(raw[hb][i]), us, bv[i]);
+          out[i] = softplus100_scaled(zs, e);
+          const float r = mufu_rcp(1.0f + e);
+          sg[i] = (zs >= 0.f) ? r : e * r;
+        }
+        __stcg(reinterpret_cast<uint4*>(R.sig + (size_t)l * kRowStride + n0),
+               make_uint4(unorm16_pack2(sg[0], sg[1]), unorm16_pack2(sg[2], sg[3]), unorm16_pack2(sg[4], sg[5]), unorm16_pack2(sg[6], sg[7])));
+        if (SPEC == 1 && n0 + 8 > 217) {
+          const Embed8 ev = embed8<3, false>(n0 - 217, kEmbed, E.px, E.py, E.pz, 0.f, a.embed_w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) out[i] = ((ev.ok >> i) & 1u) ? kTcScaleA * ev.v[i] : out[i];
+        }
+        if (SPEC == 2) E.head0 += head_dot8(a.w_last + n0, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+      } else {
+        // softplus' of this hand-off's 8 columns (times 65535; the scale is folded below)
+        const float sv[8] = {unorm16_lo(sqv.x), unorm16_hi(sqv.x), unorm16_lo(sqv.y), unorm16_hi(sqv.y),
+                             unorm16_lo(sqv.z), unorm16_hi(sqv.z), unorm16_lo(sqv.w), unorm16_hi(sqv.w)};
+        if (KIND == 1) {
+          if (E.valid) {   // the 256-d feature vector: written once, read once by the colour net -> streaming stores
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(raw[hb][i]), us, bv[i]);
+            float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)E.p * kFeat + n0);
+            __stcs(dst, make_float4(f[0], f[1], f[2], f[3]));
+            __stcs(dst + 1, make_float4(f[4], f[5], f[6], f[7]));
+          }
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          // g_7 = w_sdf * s_7, times the operand scale
+#pragma unroll
+          for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * wv[i] * sv[i];
+        } else {
+          if (KIND == 2) {   // operand of the next backward layer: (acc * unscale) * s_{l-1}, times the operand scale (one constant)
+            const float k2 = us * (kTcScaleA * kInvQ);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[i] = (__uint_as_float(raw[hb][i]) * k2) * sv[i];
+          }
+          if ((KIND == 2 && SPEC == 1 && n0 + 8 > 217) || (KIND == 3 && n0 < 40)) {  // columns that are d sdf / d embed
+            const int e0 = (KIND == 2) ? n0 - 217 : n0;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[hb][i]) * us;
+            const Embed8 dv = embed8<3, true>(e0, kEmbed, E.px, E.py, E.pz, 0.f, a.embed_w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ec = max(e0 + i, 0), d = ec - 3 * ((ec * 171) >> 9);
+              const bool ok = (dv.ok >> i) & 1u;
+              const float je = ok ? acc[i] * dv.v[i] : 0.f;
+              E.head1 += (d == 0) ? je : 0.f;
+              E.head2 += (d == 1) ? je : 0.f;
+              R.gz += (d == 2) ? je : 0.f;
+              if (KIND == 2) out[i] = ok ? 0.f : out[i];
+            }
+          }
+        }
+      }
+      if (KIND != 3) {
+        uint4 hi, lo;
+        split8(out, hi, lo);
+        uint8_t* dst = E.a_row + c * kTcAChunkBytes + (hb ? (E.u0 ^ 64u) : E.u0);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + E.lo_off) = lo;
+        handoff_arrive(E.bAReady + 16 * c + 8 * hb, E.lane);
+      }
+    }
+  }
+  return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
   static_assert(MODE == MLP_SDF_ONLY || MODE == MLP_SDF_REV || MODE == MLP_COLOR || MODE == MLP_BG_SDF || MODE == MLP_BG_RGB || MODE == MLP_LINEAR, "chains built on tcgen05");
@@ -761,138 +897,26 @@ __global__ void __launch_bounds__(kTcThreadsTotal, 1) k_mlp_tc(TcArgs a) {
         continue;
       }
       if (MODE == MLP_SDF_REV) {
-        // ======== reverse-mode gradient: 8 forward layers (stash softplus'), feature layer, 8 backward layers ========
-        // d sdf/d z_7 = w_sdf * s_7;  d sdf/d z_{l-1} = (g_l . W_l) * s_{l-1};  embedding columns (skip input of
-        // layer 4, input of layer 0) collect d sdf/d embed, chained with d embed/d x_c per column.
-        // Stash: s_l = softplus'(z_l) as unorm16, written and later read by the SAME thread (row, 8 columns per hand-off), L2
-        // only (.cg): 512 KB per CTA.  Reads run two hand-offs ahead of their use (an L2 round trip is ~1 hand-off long).
-        uint16_t* sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
-        constexpr float kInvQ = 1.0f / 65535.0f;
-        bool rev_ok = true;
-        for (int st = 0; st < 17 && rev_ok; ++st) {
-          const int kind = (st < 8) ? 0 : ((st == 8) ? 1 : ((st < 16) ? 2 : 3));
-          const int l = (st <= 8) ? st : 16 - st;
-          const float* bias = (kind <= 1) ? a.L[st].bias : nullptr;
-          // stash row read by this step: s_7 for the feature layer's seed, s_{l-1} for backward layer l
-          const uint16_t* srow = (kind == 1) ? sig + (size_t)7 * (kTcRows * 256) : ((kind == 2) ? sig + (size_t)(l - 1) * (kTcRows * 256) : nullptr);
-          float4 nb0 = make_float4(0.f, 0.f, 0.f, 0.f), nb1 = nb0;
-          uint4 sq0 = make_uint4(0u, 0u, 0u, 0u), sq1 = sq0;
-          if (bias != nullptr) {
-            nb0 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8));
-            nb1 = __ldg(reinterpret_cast<const float4*>(bias + sub * 8) + 1);
+        // ======== reverse-mode gradient: 8 forward layers (stash softplus'), feature layer, 8 backward layers (rev_step) ========
+        {
+          EpiState E;
+          E.bAReady = bAReady, E.bDFull = bDFull, E.t_lane = t_lane;
+          E.a_row = gA_hi + (row >> 3) * 1024 + (row & 7) * 128;
+          E.u0 = (uint32_t)((sub ^ (row & 7)) << 4), E.lo_off = (uint32_t)(NA * kTcAChunkBytes);
+          E.sub = sub, E.lane = lane, E.p = p, E.valid = valid;
+          E.px = px, E.py = py, E.pz = pz, E.pw = 0.f;
+          E.head0 = 0.f, E.head1 = 0.f, E.head2 = 0.f, E.d_par = d_par, E.abort_flag = abort_flag;
+          RevState R;
+          R.sig = a.sig + (size_t)blockIdx.x * (8 * kTcRows * 256) + (size_t)row * 256;
+          R.gz = 0.f;
+          bool ok = true;
+          for (int st = 0; st < 17 && ok; ++st) {
+            if (st < 8) ok = (st == 3) ? rev_step<0, 1>(a, E, R, st) : ((st == 7) ? rev_step<0, 2>(a, E, R, st) : rev_step<0, 0>(a, E, R, st));
+            else if (st == 8) ok = rev_step<1, 0>(a, E, R, st);
+            else if (st < 16) ok = (st == 12) ? rev_step<2, 1>(a, E, R, st) : rev_step<2, 0>(a, E, R, st);
+            else ok = rev_step<3, 0>(a, E, R, st);
           }
-          if (srow != nullptr) {
-            sq0 = __ldcg(reinterpret_cast<const uint4*>(srow + sub * 8));
-            sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + 32 + sub * 8));
-          }
-          const uint32_t dbar = bDFull + 32 * (st & 1), dpar = (d_par >> (st & 1)) & 1;
-          if (!mbar_wait(dbar, dpar, a.err, 4, abort_flag)) break;
-          d_par ^= (1u << (st & 1));
-          tc_fence_after();
-          const uint32_t t_col = t_lane + (uint32_t)((st & 1) * 256 + sub * 8);
-          uint32_t raw[8];
-          tc_ld8(t_col, raw);
-#pragma unroll 2
-          for (int h = 0; h < 8; ++h) {
-            const int n0 = h * 32 + sub * 8;
-            const float bv[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
-            if (bias != nullptr && h + 1 < 8) {
-              nb0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32));
-              nb1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 32) + 1);
-            }
-            const uint4 sq = sq0;
-            sq0 = sq1;
-            if (srow != nullptr && h + 2 < 8) sq1 = __ldcg(reinterpret_cast<const uint4*>(srow + n0 + 64));
-            tc_wait_ld();
-            float acc[8];
-            const float us = (kind == 0) ? a.unscale * kTcScaleA : a.unscale;   // forward layers work on kTcScaleA * z (bias pre-scaled)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = __uint_as_float(raw[i]) * us;
-            if ((h & 1) && h + 1 < 8) {   // the next hand-off opens the accumulator's next 64-column quarter
-              if (!mbar_wait(dbar + 8 * ((h + 1) >> 1), dpar, a.err, 4, abort_flag)) { rev_ok = false; break; }
-              tc_fence_after();
-            }
-            if (h + 1 < 8) tc_ld8(t_col + (uint32_t)((h + 1) * 32), raw);
-            float out[8];
-            if (kind == 0) {
-              float sg[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e;
-                const float z = acc[i] + bv[i];
-                out[i] = softplus100_scaled(z, e);
-                const float r = mufu_rcp(1.0f + e);
-                sg[i] = (z >= 0.f) ? r : e * r;
-              }
-              __stcg(reinterpret_cast<uint4*>(sig + (size_t)l * (kTcRows * 256) + n0),
-                     make_uint4(unorm16_pack2(sg[0], sg[1]), unorm16_pack2(sg[2], sg[3]), unorm16_pack2(sg[4], sg[5]), unorm16_pack2(sg[6], sg[7])));
-              if (l == 3 && n0 + 8 > 217) {
-                const Embed8 ev = embed8<3, false>(n0 - 217, kEmbed, px, py, pz, 0.f, a.embed_w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) out[i] = ((ev.ok >> i) & 1u) ? kTcScaleA * ev.v[i] : out[i];
-              }
-              if (l == 7) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + i);
-                  head0 += out[4 * i] * w0.x + out[4 * i + 1] * w0.y + out[4 * i + 2] * w0.z + out[4 * i + 3] * w0.w;
-                }
-              }
-            } else {
-              // softplus' of this hand-off's 8 columns (times 65535; the scale is folded below)
-              const float sv[8] = {unorm16_lo(sq.x), unorm16_hi(sq.x), unorm16_lo(sq.y), unorm16_hi(sq.y),
-                                   unorm16_lo(sq.z), unorm16_hi(sq.z), unorm16_lo(sq.w), unorm16_hi(sq.w)};
-              if (kind == 1) {
-                if (valid) {   // the 256-d feature vector: written once, read once by the colour net -> streaming stores
-                  float4* dst = reinterpret_cast<float4*>(a.feat + (size_t)p * kFeat + n0);
-                  __stcs(dst, make_float4(acc[0] + bv[0], acc[1] + bv[1], acc[2] + bv[2], acc[3] + bv[3]));
-                  __stcs(dst + 1, make_float4(acc[4] + bv[4], acc[5] + bv[5], acc[6] + bv[6], acc[7] + bv[7]));
-                }
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w_last + n0) + 1);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                // g_7 = w_sdf * s_7, times the operand scale
-#pragma unroll
-                for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * wv[i] * sv[i];
-              } else if (kind == 2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) out[i] = (kTcScaleA * kInvQ) * acc[i] * sv[i];
-                if (l == 4 && n0 + 8 > 217) {  // skip input of layer 4: columns 217.. are d sdf / d embed
-                  const Embed8 dv = embed8<3, true>(n0 - 217, kEmbed, px, py, pz, 0.f, a.embed_w);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int ec = max(n0 + i - 217, 0), d = ec - 3 * ((ec * 171) >> 9);
-                    const bool ok = (dv.ok >> i) & 1u;
-                    const float je = ok ? acc[i] * dv.v[i] : 0.f;
-                    head1 += (d == 0) ? je : 0.f;
-                    head2 += (d == 1) ? je : 0.f;
-                    gz_acc += (d == 2) ? je : 0.f;
-                    out[i] = ok ? 0.f : out[i];
-                  }
-                }
-              } else {  // kind 3: d sdf / d embed through layer 0's input
-                if (n0 < 40) {
-                  const Embed8 dv = embed8<3, true>(n0, kEmbed, px, py, pz, 0.f, a.embed_w);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int e = n0 + i, d = e - 3 * ((e * 171) >> 9);
-                    const float je = ((dv.ok >> i) & 1u) ? acc[i] * dv.v[i] : 0.f;
-                    head1 += (d == 0) ? je : 0.f;
-                    head2 += (d == 1) ? je : 0.f;
-                    gz_acc += (d == 2) ? je : 0.f;
-                  }
-                }
-              }
-            }
-            if (st < 16) {
-              uint4 hi, lo;
-              split8(out, hi, lo);
-              const int c = h >> 1, j = (h & 1) * 4 + sub;
-              *reinterpret_cast<uint4*>(gA_hi + c * kTcAChunkBytes + a_unit_off(row, j)) = hi;
-              *reinterpret_cast<uint4*>(gA_lo + c * kTcAChunkBytes + a_unit_off(row, j)) = lo;
-              handoff_arrive(bAReady + 8 * h, lane);
-            }
-          }
+          d_par = E.d_par, head0 = E.head0, head1 = E.head1, head2 = E.head2, gz_acc = R.gz;
         }
         // fixed-order reduction of (sdf head, d/dx, d/dy, d/dz) over the quarter's 4 warps
         tc_fence_before();

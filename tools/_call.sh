@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_sampler_rounds.py tests/test_gpu_stages.py tests/test_gpu_e2e.py tests/test_gpu_edges.py -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -3
-timeout 900 python bench.py --no-extras 2>gpurun_out/r3f_bench.err | tee gpurun_out/r3f_bench.json | cut -c1-260
+for n in 101 0 101 0; do timeout 300 python tools/exp_epilogue.py --run $n 2>&1 | grep "^exp"; done | tee gpurun_out/r3g_exp_rev.log
+timeout 1200 python -m pytest tests/test_gpu_tc.py tests/test_gpu_stages.py tests/test_gpu_e2e.py tests/test_gpu_edges.py -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -3
