@@ -404,7 +404,11 @@ __device__ __forceinline__ bool epi_layer(const TcArgs& a, EpiState& E, const in
   const float us = FEAT ? a.unscale : a.unscale * kTcScaleA;
   uint32_t raw[2][8];
   tc_ld8(t_col, raw[0]);
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 12   // timing experiment: four hand-offs per loop iteration
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
   for (int c = 0; c < 4; ++c) {
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
@@ -506,7 +510,11 @@ __device__ __forceinline__ bool rev_step(const TcArgs& a, EpiState& E, RevState&
   const float us = (KIND == 0) ? a.unscale * kTcScaleA : a.unscale;   // forward layers work on kTcScaleA * z (bias pre-scaled)
   uint32_t raw[2][8];
   tc_ld8(t_col, raw[0]);
+#if defined(HOLD_TC_EXP) && HOLD_TC_EXP == 12   // timing experiment: four hand-offs per loop iteration
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
   for (int c = 0; c < 4; ++c) {
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {

@@ -1,12 +1,12 @@
 """Timing experiments on the tcgen05 epilogue (never part of the product build): variants of libhold_b200.so compiled with
 -DHOLD_TC_EXP=n knock one ingredient out of the forward epilogue (results are then WRONG; only the time is read):
-  1 no MUFU, 2 one MUFU, 3 no fence.proxy.async, 4 no hi/lo split, 5 no bias loads, 6 = 1 + 3 + 4 + 5 (accumulator -> FFMA -> store -> arrive only); 11 two weight stages instead of three; 0 = the product kernel.
+  1 no MUFU, 2 one MUFU, 3 no fence.proxy.async, 4 no hi/lo split, 5 no bias loads, 6 = 1 + 3 + 4 + 5 (accumulator -> FFMA -> store -> arrive only); 11 two weight stages instead of three, 12 hand-off loops unrolled by four; 0 = the product kernel.
   python tools/exp_epilogue.py --build      (authoring container: nvcc, writes build_exp/libhold_exp<n>.so)
   python tools/exp_epilogue.py --run n      (GPU box: times the sdf-only launch on 2^22 points)"""
 import os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 11]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 11, 12]
 OUT = os.path.join(ROOT, "build_exp")
 
 
