@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "embed_phases.h"
 #include "mlp_simt.cuh"
 
 namespace hold {
@@ -236,68 +237,6 @@ __device__ __forceinline__ uint32_t unorm16_pack2(float s0, float s1) {
 }
 __device__ __forceinline__ float unorm16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8388608.0f; }
 __device__ __forceinline__ float unorm16_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8388608.0f; }
-
-// sin and cos of x for |x| < ~1e4 (the embeddings' arguments are coordinate * 2^k, k <= 9, |coordinate| <= a few): two-constant
-// Cody-Waite reduction by pi/2 with FMAs, Taylor kernels on [-pi/4, pi/4]; max abs error 7.1e-8 over the range used (libm's sinf:
-// 3.3e-8; the pin against the oracle's torch.sin is the stage tests' 1e-4).  No slow path, no calls: eight of these run
-// interleaved per epilogue hand-off.  (The libm sinf / cosf calls this replaces sat behind a non-inlined function and cost ~500
-// clocks EACH, serially, on the critical path of every tile's prologue and skip layer: 13 % of the sdf-only kernel.)
-__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
-  const float k = rintf(x * 0.63661977236758134f);
-  float r = fmaf(k, -1.57079637050628662109375f, x);
-  r = fmaf(k, 4.371138828673793e-8f, r);
-  const float r2 = r * r;
-  float sp = fmaf(r2, 2.7557319e-6f, -1.9841270e-4f);
-  sp = fmaf(sp, r2, 8.3333333e-3f);
-  sp = fmaf(sp, r2, -1.6666667e-1f);
-  sp = fmaf(sp * r2, r, r);
-  float cp = fmaf(r2, -2.7557319e-7f, 2.4801587e-5f);
-  cp = fmaf(cp, r2, -1.3888889e-3f);
-  cp = fmaf(cp, r2, 4.1666667e-2f);
-  cp = fmaf(cp, r2, -0.5f);
-  cp = fmaf(cp, r2, 1.0f);
-  const int q = __float2int_rn(k);
-  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
-  s = (q & 2) ? -ss : ss;
-  c = ((q + 1) & 2) ? -cc : cc;
-}
-
-// Eight consecutive elements e0 .. e0+7 of the Fourier embedding (engine/embedders.py:48-51: [x, sin(2^0 x), cos(2^0 x), sin(2^1 x),
-// ...], D coordinates per point, n_embed elements) or, DERIV, of its derivative w.r.t. the element's own coordinate.  Branch-free:
-// the eight sin/cos chains interleave (per-element branches serialise them: ~3 k clocks per hand-off on the tile's critical path).
-// ew: optional per-element weights (BarfEmbedder).  Returns the mask of elements that exist (0 <= e < n_embed); v[i] is finite
-// garbage elsewhere.
-template <int D, bool DERIV>
-__device__ __forceinline__ uint32_t embed8_inl(int e0, int n_embed, float x0, float x1, float x2, float x3, const float* __restrict__ ew,
-                                               float (&v)[8]) {
-  uint32_t okm = 0;
-  float w[8];
-  if (ew != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = __ldg(ew + min(max(e0 + i, 0), n_embed - 1));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = 1.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int e = e0 + i;
-    const bool ok = (unsigned)e < (unsigned)n_embed;
-    const int ec = ok ? e : 0;
-    const int g = (D == 4) ? (ec >> 2) : ((ec * 171) >> 9);   // ec / D (ec < 256)
-    const int d = ec - D * g;
-    const int qq = g - 1;                                     // -1: the identity block
-    const float pc = (d == 0) ? x0 : ((d == 1) ? x1 : ((d == 2 || D == 3) ? x2 : x3));
-    const float f = __int_as_float((127 + (max(qq, 0) >> 1)) << 23);
-    float sn, cs;
-    sincos_cw(pc * f, sn, cs);
-    float r = DERIV ? ((qq & 1) ? -f * sn : f * cs) : ((qq & 1) ? cs : sn);
-    r = (qq < 0) ? (DERIV ? 1.f : pc) : r;
-    v[i] = r * w[i];
-    okm |= ok ? (1u << i) : 0u;
-  }
-  return okm;
-}
 
 // (Measured, profiles/r02_epilogue_experiments.md: making this and the head dot products out-of-line functions behind one
 // shared epilogue body -- to shrink the kernel from 49 KB to 28 KB of code -- was 5 % SLOWER than one specialised body per layer
