@@ -302,6 +302,28 @@ class Node(nn.Module):
     def embed_w(self):
         return self.barf_weights
 
+    def start_barf(self, start=1000, end=10000):
+        """Training-mode coarse-to-fine mask of the object's embedder (engine/embedders.py:53-126, BarfEmbedder; parser.py:32-33
+        barf_s / barf_e): frequency k of the 6 is weighted clamp(alpha - k, 0, 1) with a cosine ramp inside (0, 1), alpha follows
+        [0]*start + linspace(0, 6, end - start) and advances once per training forward (step_embedding).  Hands and the background
+        use the plain Fourier embedder (model/*/specs.py), whose step() does nothing."""
+        assert self.kind == "object", "only the object's ImplicitNet uses the BARF embedder (model/obj/specs.py:10)"
+        self._barf = BarfSchedule(6, 3, start, end)
+        self.barf_weights = self._barf.weights().to(self.density.beta.device)
+
+    def step_embedding(self):
+        """Node.step_embedding (node.py:108-109)."""
+        sched = getattr(self, "_barf", None)
+        if sched is not None:
+            sched.step()
+            self.barf_weights = sched.weights().to(self.density.beta.device)
+
+    def eval(self):
+        """BarfEmbedder.eval(): no_barf = True -> all frequencies pass (embedders.py:124-125, render.py:43-47)."""
+        if getattr(self, "_barf", None) is not None:
+            self.barf_weights = None
+        return super().eval()
+
     def sync_weights(self):
         """Re-pack the (possibly updated) parameters into the library (hold_node_set_weights)."""
         isd = {k: v for k, v in self.implicit_network.state_dict().items()}
@@ -412,6 +434,26 @@ class Background(nn.Module):
         return out
 
 
+class BarfSchedule:
+    """alpha schedule + weights of engine/embedders.py:53-106 (BarfEmbedder.__init__, compute_barf_weights, step)."""
+
+    def __init__(self, num_freq, input_dims, start, end):
+        self.L, self.D = num_freq, input_dims
+        self.alphas = torch.cat((torch.zeros(start), torch.linspace(0, num_freq, end - start)), 0)
+        self.alpha_iter = 0
+
+    def step(self):
+        self.alpha_iter = min(self.alpha_iter + 1, len(self.alphas) - 1)
+
+    def weights(self):
+        ak = self.alphas[self.alpha_iter] - torch.arange(self.L, dtype=torch.float32)
+        w = torch.clamp(ak, 0, 1)
+        ramp = torch.logical_and(0 <= ak, ak < 1)
+        w[ramp] = ((1 - torch.cos(ak * math.pi)) / 2)[ramp]
+        w = w[:, None].repeat(1, self.D * 2).view(-1)       # sin and cos of every coordinate share the frequency's weight
+        return torch.cat((torch.ones(self.D), w), 0).contiguous()
+
+
 class HOLDNet(nn.Module):
     """hold/hold_net.py:23-134, foreground: nodes{right,left,object}; forward_fg(input) -> out dict with the
     reference's keys (fg_rgb, mask_prob, normal, depth, fg_semantics, fg_weights, bg_weights, <node>.*, ray_dirs, cam_loc)."""
@@ -421,6 +463,11 @@ class HOLDNet(nn.Module):
         self.ctx = ctx
         self.nodes = nn.ModuleDict(nodes)
         self.background = background
+
+    def step_embedding(self):
+        """hold_net.py:104-108 (the background's Fourier embedders have nothing to step)."""
+        for n in self.nodes.values():
+            n.step_embedding()
 
     def sync_weights(self):
         for n in self.nodes.values():

@@ -695,6 +695,8 @@ def forward_train(net, input, generator=None):
         rgb, sem = rgb + bgo["bg_rgb"], sem + bgo["bg_semantics"]
         out["bg_rgb_only"] = bgo["bg_rgb_only"]
     out["rgb"], out["semantics"] = rgb, sem
+    if hasattr(net, "step_embedding"):
+        net.step_embedding()                                                # hold_net.py:121-122: the BARF counter advances per training forward
     return out
 
 

@@ -428,6 +428,25 @@ def golden_loss():
         print("wrote", path, {k: float(v) for k, v in ld.items()})
 
 
+def golden_barf():
+    """tests/golden/barf_weights.pt: BARF weights of the REFERENCE's BarfEmbedder (engine/embedders.py:53-126) along its schedule."""
+    from src.engine.embedders import BarfEmbedder
+
+    rec = {}
+    for start, end in ((5, 25), (1000, 10000)):
+        e = BarfEmbedder(3, 6, start, end, "cpu")
+        its = sorted({0, start, start + 1, (start + end) // 2, end - 2, end - 1, end + 50})
+        w = {}
+        for it in range(max(its) + 1):
+            if it in its:
+                w[it] = e.barf_weights.clone()
+            e.step()
+        rec[(start, end)] = w
+    path = os.path.join(REPO, "tests", "golden", "barf_weights.pt")
+    torch.save(rec, path)
+    print("wrote", path)
+
+
 def golden():
     """tests/golden/*.pt: inputs are regenerated from the seed; outputs come from the REFERENCE modules."""
     from hold_b200 import synth
@@ -474,3 +493,5 @@ if __name__ == "__main__":
         golden_background()
     elif cmd == "golden_loss":
         golden_loss()
+    elif cmd == "golden_barf":
+        golden_barf()
