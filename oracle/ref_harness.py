@@ -429,7 +429,7 @@ def golden_loss():
 
 
 def golden_barf():
-    """tests/golden/barf_weights.pt: BARF weights of the REFERENCE's BarfEmbedder (engine/embedders.py:53-126) along its schedule."""
+    """tests/golden/barf/barf_weights.pt: BARF weights of the REFERENCE's BarfEmbedder (engine/embedders.py:53-126) along its schedule."""
     from src.engine.embedders import BarfEmbedder
 
     rec = {}
@@ -442,7 +442,8 @@ def golden_barf():
                 w[it] = e.barf_weights.clone()
             e.step()
         rec[(start, end)] = w
-    path = os.path.join(REPO, "tests", "golden", "barf_weights.pt")
+    path = os.path.join(REPO, "tests", "golden", "barf", "barf_weights.pt")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
     torch.save(rec, path)
     print("wrote", path)
 

@@ -1,5 +1,5 @@
 """hold_b200.model.BarfSchedule against the weights the REFERENCE's BarfEmbedder holds along its schedule
-(tests/golden/barf_weights.pt, written by `python oracle/ref_harness.py golden_barf`)."""
+(tests/golden/barf/barf_weights.pt, written by `python oracle/ref_harness.py golden_barf`)."""
 import os
 
 import torch
@@ -8,7 +8,7 @@ import torch
 def test_barf_schedule_matches_reference_embedder():
     from hold_b200.model import BarfSchedule
 
-    rec = torch.load(os.path.join(os.path.dirname(__file__), "golden", "barf_weights.pt"))
+    rec = torch.load(os.path.join(os.path.dirname(__file__), "golden", "barf", "barf_weights.pt"))
     for (start, end), ws in rec.items():
         s = BarfSchedule(6, 3, start, end)
         for it in range(max(ws) + 1):
