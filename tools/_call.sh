@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | grep -v "Warning\|kaiming\|WeightNorm" | tail -3
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep "smoke OK\|rror"
-timeout 1200 python bench.py 2>gpurun_out/r3i_bench.err | tee gpurun_out/r3i_bench.json | cut -c1-260
-timeout 600 python bench.py --config train --steps 10 --warmup 5 2>gpurun_out/r3i_train.err | tee gpurun_out/r3i_train.json | cut -c1-200
+for n in 0 12 0 12; do timeout 300 python tools/exp_epilogue.py --run $n 2>&1 | grep "^exp"; done | tee gpurun_out/r3j_exp_unroll.log
