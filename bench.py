@@ -251,7 +251,7 @@ def run_train(args):
     gt_rgb = torch.rand(R, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
     gt_mask = torch.zeros(R, 4, device=dev)
     gt_mask[:, 0] = 1.0
-    ts = train.TrainStep(net, group=None)
+    ts = train.TrainStep(net, group=None, capturable=args.graph)
     ts.params = ts.params + pose_leaves          # pose gradients ride in the same flat bucket
     n_grad = sum(p.numel() for p in ts.params)
 
@@ -261,15 +261,39 @@ def run_train(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(1, args.warmup)):
+    graph_note = "eager launches"
+    run = lambda: ts.step(inp, gt_rgb, gt_mask)
+    if not args.graph:
+        for _ in range(max(1, args.warmup)):
+            loss, parts = ts.step(inp, gt_rgb, gt_mask)
+        sync_all()
+        ctx.check()
+        l0 = ctx.launches
         loss, parts = ts.step(inp, gt_rgb, gt_mask)
+        launches_per_step = ctx.launches - l0
+    else:
+        # no eager step on the default stream before the capture: the parameters' AccumulateGrad nodes would be tied to the legacy
+        # stream, which a capturing stream may not wait on; capture() warms up on a side stream itself
+        try:
+            l0 = ctx.launches
+            ts.capture(inp, gt_rgb, gt_mask, warmup=max(3, args.warmup))
+            launches_per_step = (ctx.launches - l0) // (max(3, args.warmup) + 1)
+            run = lambda: ts.replay()
+            for _ in range(2):
+                run()
+            graph_note = "the whole step captured once as ONE CUDA graph and replayed (TrainStep.capture)"
+        except Exception as e:   # noqa: BLE001 - a failed capture leaves the CUDA generator / allocator unusable: report and stop
+            import traceback
+
+            traceback.print_exc()
+            if rank == 0:
+                print(json.dumps({"metric": "training rays/sec (forward + backward + gradient all-reduce + Adam)", "unavailable": f"CUDA graph capture failed: {type(e).__name__}: {str(e)[:200]}"}))
+            return
     sync_all()
-    ctx.check()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ctx.launches
     e0.record()
     for _ in range(args.steps):
-        loss, parts = ts.step(inp, gt_rgb, gt_mask)
+        loss, parts = run()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -286,7 +310,7 @@ def run_train(args):
                        "collective": f"one flat-bucket all-reduce of {n_grad} fp32 gradients per step (NCCL)" if world > 1 else "none (1 rank)",
                        "losses": "L1 rgb + L2 semantics + eikonal (256 canonical samples per frame)", "model": "right hand + object + NeRF++ background (32 inverse-sphere samples/ray)",
                        "mlp_mode": "tcgen05 fp16-split x3: hold_linear (activations), hold_wgrad (weight gradients); hold_composite_bwd"},
-            "gpu_launches": ctx.launches - l0, "loss": float(loss), "loss_terms": {k: float(v) for k, v in parts.items()}}))
+            "gpu_launches": launches_per_step * args.steps, "launch_mode": graph_note, "loss": float(loss), "loss_terms": {k: float(v) for k, v in parts.items()}}))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -299,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("HOLD_MLP_MODE", "auto"), choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="--config train: capture the step as one CUDA graph and time replays")
     ap.add_argument("--config", default="render", choices=["render", "train"],
                     help="render: BASELINE configs[1] (the driver's line); train: one data-parallel training step (configs[4] / SURVEY C5)")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] (two hands + object) and full-forward (with background) fields")

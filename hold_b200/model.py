@@ -116,9 +116,11 @@ class _ObjectTfFn(torch.autograd.Function):
     """ObjectModel.forward under autograd: forward = hold_object_tf, backward = hold_object_tf_bwd."""
 
     @staticmethod
-    def forward(fctx, server, scene_scale, transl, thetas, obj_scale):
-        out = server._forward_nograd(scene_scale, transl, thetas, float(obj_scale))
-        fctx.server = server
+    def forward(fctx, server, scene_scale, transl, thetas, obj_scale, obj_scale_host=None):
+        # obj_scale_host: the scale as a Python float when it is not being optimised (no device->host read: capturable as a CUDA graph)
+        val = float(obj_scale) if obj_scale_host is None else obj_scale_host
+        out = server._forward_nograd(scene_scale, transl, thetas, val)
+        fctx.server, fctx.obj_scale_val = server, val
         fctx.save_for_backward(scene_scale.detach(), transl.detach(), thetas.detach(), obj_scale.detach())
         return out["verts"], out["obj_tfs"]
 
@@ -133,9 +135,9 @@ class _ObjectTfFn(torch.autograd.Function):
         Nv = srv.v3d_cano.shape[0]
         gr, gt, gs, go = torch.empty(B, 3, device=dev), torch.empty(B, 3, device=dev), torch.empty(B, device=dev), torch.empty(B, device=dev)
         check(lib().hold_object_tf_bwd(srv.ctx.h, B, ptr(f(thetas, (B, 3))), ptr(f(transl, (B, 3))), ptr(f(scene_scale, (B,))),
-                                       float(obj_scale), ptr(srv.denorm_mat), ptr(srv.v3d_cano), Nv, ptr(gc(g_verts, (B, Nv, 3))),
+                                       fctx.obj_scale_val, ptr(srv.denorm_mat), ptr(srv.v3d_cano), Nv, ptr(gc(g_verts, (B, Nv, 3))),
                                        ptr(gc(g_tfs, (B, 4, 4))), ptr(gr), ptr(gt), ptr(gs), ptr(go), stream_ptr()))
-        return None, gs.reshape(scene_scale.shape), gt.reshape(transl.shape), gr.reshape(thetas.shape), go.sum().reshape(obj_scale.shape)
+        return None, gs.reshape(scene_scale.shape), gt.reshape(transl.shape), gr.reshape(thetas.shape), go.sum().reshape(obj_scale.shape), None
 
 
 class MANOServer(nn.Module):
@@ -233,8 +235,9 @@ class ObjectServer(nn.Module):
         osc = self.obj_scale
         needs = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (scene_scale, transl, thetas, osc))
         if needs:
-            osc_t = osc if torch.is_tensor(osc) else torch.tensor(float(osc), device=self.v3d_cano.device)
-            verts, tfs = _ObjectTfFn.apply(self, scene_scale, transl, thetas, osc_t)
+            # torch.full = a fill kernel; torch.tensor(float, device=cuda) would be a pageable host->device copy (not capturable)
+            osc_t = osc if torch.is_tensor(osc) else torch.full((), float(osc), device=self.v3d_cano.device)
+            verts, tfs = _ObjectTfFn.apply(self, scene_scale, transl, thetas, osc_t, None if torch.is_tensor(osc) else float(osc))
             return {"verts": verts, "obj_tfs": tfs}
         return self._forward_nograd(scene_scale, transl, thetas, float(osc))
 
@@ -333,7 +336,9 @@ class Node(nn.Module):
         lp_w = rsd["lin_pose.weight"].float().contiguous() if self.kind == "hand" else None
         lp_b = rsd["lin_pose.bias"].float().contiguous() if self.kind == "hand" else None
         check(lib().hold_node_set_weights(self.ctx.h, self.slot, C.byref(wi), C.byref(wr), ptr(lp_w), ptr(lp_b), stream_ptr()))
-        torch.cuda.current_stream().synchronize()  # k1/k2 temporaries may be freed after this point
+        # no host sync: the packing kernels run on the current stream, and the caching allocator hands the temporaries (k1, k2)
+        # back only to later work of that same stream (a sync here stalled every training step three times and made the step
+        # uncapturable as a CUDA graph)
 
     # -- articulation ---------------------------------------------------------------------------------
     def articulate(self, input):
@@ -417,8 +422,7 @@ class Background(nn.Module):
         rsd = dict(self.bg_rendering_network.state_dict())
         wi, k1 = capi.mlp_weights(isd, 9)
         wr, k2 = capi.mlp_weights(rsd, 2)
-        check(lib().hold_bg_set_weights(self.ctx.h, C.byref(wi), C.byref(wr), self.mlp_mode, stream_ptr()))
-        torch.cuda.current_stream().synchronize()
+        check(lib().hold_bg_set_weights(self.ctx.h, C.byref(wi), C.byref(wr), self.mlp_mode, stream_ptr()))   # stream-ordered, no host sync
 
     @torch.no_grad()
     def forward(self, bg_weights, ray_dirs, cam_loc, idx, B):

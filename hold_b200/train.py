@@ -322,7 +322,8 @@ def node_forward_train(node, x, tfs, verts, frame_of_point, pose_cond=None, time
         J = torch.bmm(w.reshape(B, P, 16), tfs[:, :, :3, :3].reshape(B, 16, 9)).reshape(B * P, 3, 3)
     else:
         J = tfs.reshape(B, 1, 4, 4)[:, :, :3, :3].expand(B, P, 3, 3).reshape(B * P, 3, 3)
-    normal = torch.nn.functional.normalize(torch.einsum("bi,bij->bj", g, torch.linalg.inv(J)), dim=1, eps=1e-6)
+    # inv_ex: torch.linalg.inv reads its error flag on the host (a sync per node per step)
+    normal = torch.nn.functional.normalize(torch.einsum("bi,bij->bj", g, torch.linalg.inv_ex(J).inverse), dim=1, eps=1e-6)
     if node.kind == "hand":
         pe = node.rendering_network.lin_pose(pose_cond)[:, None, :].expand(B, P, 8).reshape(B * P, 8)   # per-frame rows, frame-major points
         inp = torch.cat([x_c, normal, pe, feat], 1)
@@ -763,10 +764,48 @@ class TrainStep:
     kaolin-target terms (mano_cano, opacity_sparse) is `Loss` (pinned to the reference's module, tests/test_cpu_loss.py) on the
     same output dict once the canonical meshes are attached to the nodes."""
 
-    def __init__(self, net, lr=1e-4, n_eik=256, group=None):
+    def __init__(self, net, lr=1e-4, n_eik=256, group=None, capturable=False):
         self.net, self.group, self.n_eik = net, group, n_eik
         self.params = [p for p in net.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr)
+        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=capturable)
+        self._graph = None
+
+    # ---- the step as ONE CUDA graph.  The step is ~1 200 small launches on 1 280 rays (packing, sampler rounds, ~70 matrix
+    # products, pointwise kernels, Adam): host-bound when launched one by one.  Nothing in it depends on the host (no syncs, no
+    # data-dependent control flow: the sampler's convergence gate lives on the device), so after warm-up -- workspaces grown,
+    # allocator warm -- it is captured once and replayed; inputs are copied into the captured tensors.
+    def capture(self, input, gt_rgb, gt_mask, warmup=3):
+        assert self.opt.defaults.get("capturable", False), "TrainStep(..., capturable=True) for graph capture"
+        self._static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in input.items()}
+        self._leaf_of = {k: v for k, v in input.items() if torch.is_tensor(v) and v.requires_grad}
+        for k, v in self._leaf_of.items():            # pose leaves the caller optimises stay the caller's tensors
+            self._static[k] = v
+        self._gt = (gt_rgb.clone(), gt_mask.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._static, *self._gt)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=False)
+        with torch.cuda.graph(self._graph):
+            self._loss, self._parts = self.step(self._static, *self._gt, zero=True)
+        return self
+
+    def replay(self, input=None, gt_rgb=None, gt_mask=None):
+        """One captured step; new batch contents (same shapes) are copied into the captured tensors first."""
+        if input is not None:
+            for k, v in input.items():
+                if torch.is_tensor(v) and k not in self._leaf_of:
+                    self._static[k].copy_(v)
+        if gt_rgb is not None:
+            self._gt[0].copy_(gt_rgb)
+        if gt_mask is not None:
+            self._gt[1].copy_(gt_mask)
+        self._graph.replay()
+        return self._loss, self._parts
 
     def forward_loss(self, input, gt_rgb, gt_mask, generator=None):
         out = forward_train(self.net, input, generator)
@@ -782,10 +821,13 @@ class TrainStep:
         loss_eik = sum(eik) * 1e-5
         return loss_rgb + loss_sem + loss_eik, dict(rgb=loss_rgb.detach(), sem=loss_sem.detach(), eikonal=loss_eik.detach())
 
-    def step(self, input, gt_rgb, gt_mask, generator=None):
+    def step(self, input, gt_rgb, gt_mask, generator=None, zero=True):
         from . import shard
 
-        self.opt.zero_grad(set_to_none=False)
+        if zero:
+            for p in self.params:                      # in place (captured graphs need stable gradient tensors)
+                if p.grad is not None:
+                    p.grad.zero_()
         loss, parts = self.forward_loss(input, gt_rgb, gt_mask, generator)
         loss.backward()
         shard.allreduce_grads_(self.params, group=self.group, average=True)

@@ -388,3 +388,42 @@ def test_forward_train_outputs_and_loss(ctx):
     assert right.implicit_network.lin4.weight_v.grad.abs().max().item() > 0
     assert bg.bg_implicit_network.lin2.weight.grad.abs().max().item() > 0
     print({k: float(v) for k, v in ld.items()})
+
+
+def test_train_step_cuda_graph_replay(ctx):
+    """TrainStep.capture / replay: the whole step as one CUDA graph gives the same losses as step-by-step launches (same
+    initial weights, same batch; weight-gradient atomics make the sums order-dependent at the 1e-6 level)."""
+    from hold_b200 import capi, scene_io, synth, train
+    from hold_b200.model import HOLDNet
+
+    def make(seed_scene=5):
+        sc = synth.make_scene(H=8, W=8, S=32, nodes=("right", "object"), B=2, seed=seed_scene)
+        sc.intrinsics[:, 0, 2] += 0.37
+        net = scene_io.build_net(sc, ctx, capi.MLP_TC)
+        bg, _, _ = scene_io.build_background(sc, ctx, mlp_mode=capi.MLP_TC)
+        return sc, HOLDNet(ctx, dict(net.nodes), background=bg)
+
+    dev = torch.device("cuda", 0)
+    sc, eager = make()
+    inp = scene_io.scene_input(sc, dev)
+    R = sc.B * sc.uv.shape[1]
+    g = torch.Generator(device=dev).manual_seed(0)
+    gt_rgb, gt_mask = torch.rand(R, 3, device=dev, generator=g), torch.zeros(R, 4, device=dev)
+    gt_mask[:, 0] = 1.0
+    torch.manual_seed(3)
+    te = train.TrainStep(eager, lr=1e-4, n_eik=64)
+    le = [te.step(inp, gt_rgb, gt_mask)[0].item() for _ in range(5)]
+    ctx.check()
+    _, graphed = make()       # same seeds -> same initial weights (the two nets share the ctx slots, used one after the other)
+    torch.manual_seed(3)
+    tg = train.TrainStep(graphed, lr=1e-4, n_eik=64, capturable=True)
+    tg.capture(inp, gt_rgb, gt_mask, warmup=3)
+    lg = [tg.replay()[0].item() for _ in range(2)]
+    ctx.check()
+    print("eager losses", le, "graph replays (steps 4, 5)", lg)
+    # the eikonal samples come from the default generator: eager steps 4, 5 and the replays draw different points, so the comparison
+    # is on the loss level the optimisation has reached, not bit for bit
+    # (Adam normalises every coordinate's step, so last-bit gradient differences -- atomics, other eikonal points -- show up at
+    # the 1e-3 level of the loss after a few steps: measured 8e-4 / 1.9e-3)
+    assert abs(lg[0] - le[3]) <= 2e-2 * abs(le[3]) and abs(lg[1] - le[4]) <= 2e-2 * abs(le[4]), (le, lg)
+    assert lg[1] < lg[0] < le[0], (le, lg)
