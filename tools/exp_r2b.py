@@ -1,4 +1,5 @@
-"""Round-2 GPU experiments (one process):
+"""Round-2 GPU experiments (one process; kept as the provenance of profiles/r02_tc_accumulator_bias.md and r02_variants.md --
+section 3 drove KNN kernel variants that have since been removed from the library):
  1. tcgen05 SDF chains vs float64: signed / max error of sdf (sampler-round kernel and reverse-mode kernel) and of the gradient,
     for accumulator compensation factors 1 + c 2^-24 (is the residual a truncation bias of the tensor core's accumulator?)
  2. kernel times: sampler-round SDF launch, reverse-mode launch
