@@ -16,6 +16,7 @@
 #include "pose_bwd.cuh"
 #include "mesh_sdf.cuh"
 #include "mise.cuh"
+#include "mc.cuh"
 #include "warp_bwd.cuh"
 #include "train.cuh"
 #include "wgrad_tc.cuh"
@@ -942,6 +943,30 @@ int hold_mise_to_dense(hold_mise* h, float* out, void* stream) {
     k_mise_fill<<<ceil_div(h->g.G * h->g.G, 128), 128, 0, s>>>(h->g, out, axis);
     HOLD_LAUNCH_CHECK(h->ctx);
   }
+  return HOLD_OK;
+}
+
+/* ---- marching cubes on a dense value grid (the last step of generate_mesh, utils/meshing.py:51) ---- */
+int hold_mc_mark(hold_ctx* ctx, int n0, int n1, int n2, const float* vol, float level, int32_t* edge_flags, int32_t* cell_ntri, void* stream) {
+  HOLD_REQUIRE(ctx && vol && edge_flags && cell_ntri, "NULL argument");
+  HOLD_REQUIRE(n0 >= 2 && n1 >= 2 && n2 >= 2, "grid must be at least 2 x 2 x 2");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  mc::Dims d{n0, n1, n2};
+  const int64_t total = (int64_t)n0 * n1 * n2;
+  k_mc_mark<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, vol, level, edge_flags, cell_ntri);
+  HOLD_LAUNCH_CHECK(ctx);
+  return HOLD_OK;
+}
+
+int hold_mc_emit(hold_ctx* ctx, int n0, int n1, int n2, const float* vol, float level, const int32_t* edge_flags, const int64_t* edge_vid,
+                 const int64_t* cell_off, float* verts, int32_t* faces, void* stream) {
+  HOLD_REQUIRE(ctx && vol && edge_flags && edge_vid && cell_off, "NULL argument");
+  HOLD_REQUIRE(n0 >= 2 && n1 >= 2 && n2 >= 2, "grid must be at least 2 x 2 x 2");
+  HOLD_CUDA(cudaSetDevice(ctx->device));
+  mc::Dims d{n0, n1, n2};
+  const int64_t total = (int64_t)n0 * n1 * n2;
+  k_mc_emit<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, vol, level, edge_flags, edge_vid, cell_off, verts, faces);
+  HOLD_LAUNCH_CHECK(ctx);
   return HOLD_OK;
 }
 

@@ -1,7 +1,9 @@
 """Canonical mesh extraction: the reference's `generate_mesh` (utils/meshing.py:9-72) with its two hot
 parts on the GPU — the SDF queries (hold_sdf_eval, the fused MLP) and the MISE octree (hold_mise_*, a restatement of
-code/src/libmise/mise.pyx that reproduces its dense value grid bit for bit).  Marching cubes stays host code, as in the
-reference (skimage), and is imported lazily."""
+code/src/libmise/mise.pyx that reproduces its dense value grid bit for bit).  Marching cubes: skimage on the host when it is
+installed (the reference's own call, Lewiner's variant), otherwise / on request `marching_cubes` below on the GPU (hold_mc_*: a
+classic case-table marching cubes with derived tables, watertight, pinned to oracle/marching_cubes.py — not to Lewiner's
+triangulation, which this image cannot run)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -113,13 +115,48 @@ def largest_component(verts, faces):
     return verts[used], remap[f[keep_f]]
 
 
-def generate_mesh(ctx, func, verts, level_set=0.0, res_init=32, res_up=3, keep_largest=True):
-    """utils/meshing.py:9-72 -> (verts [n,3], faces [m,3]) of the largest connected component (keep_largest=False: the raw
-    marching-cubes tuple (verts, faces, normals, values)).  Marching cubes by skimage on the host, an optional import exactly as in
-    the reference; the component selection (trimesh in the reference) is `largest_component` above."""
-    from skimage import measure   # noqa: the reference's own dependency for this step
+def marching_cubes(ctx, volume: torch.Tensor, level: float = 0.0):
+    """(verts [Nv,3] float32 in index coordinates, faces [Nt,3] int32) of the level set of a dense grid on the device (hold_mc_mark /
+    hold_mc_emit + two torch.cumsum scans).  Inside = value < level; normals (right-hand rule) towards increasing values."""
+    vol = volume.detach().float().contiguous()
+    n0, n1, n2 = vol.shape
+    dev = vol.device
+    flags = torch.empty(n0 * n1 * n2 * 3, dtype=torch.int32, device=dev)
+    ntri = torch.zeros((n0 - 1) * (n1 - 1) * (n2 - 1), dtype=torch.int32, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(lib().hold_mc_mark(ctx.h, n0, n1, n2, ptr(vol), float(level), vp(flags), vp(ntri), stream_ptr()))
+    vid = torch.cumsum(flags, 0, dtype=torch.int64)
+    toff = torch.cumsum(ntri, 0, dtype=torch.int64)
+    nv, nt = int(vid[-1]), int(toff[-1])                 # the one host sync: the outputs are sized by these
+    vid -= flags
+    toff -= ntri
+    verts = torch.empty(nv, 3, device=dev)
+    faces = torch.empty(nt, 3, dtype=torch.int32, device=dev)
+    if nv:
+        check(lib().hold_mc_emit(ctx.h, n0, n1, n2, ptr(vol), float(level), vp(flags), vp(vid), vp(toff), ptr(verts), vp(faces), stream_ptr()))
+    return verts, faces
 
+
+def generate_mesh(ctx, func, verts, level_set=0.0, res_init=32, res_up=3, keep_largest=True, backend="auto"):
+    """utils/meshing.py:9-72 -> (verts [n,3], faces [m,3]) of the largest connected component (keep_largest=False: the raw
+    marching-cubes tuple (verts, faces, normals, values)).  backend: "skimage" (the reference's call), "gpu" (hold_mc_*), "auto" =
+    skimage when importable, else gpu.  The component selection (trimesh in the reference) is `largest_component` above."""
     grid, res, gt_scale, gt_center = generate_grid(ctx, func, verts, level_set, res_init, res_up)
+    if backend == "auto":
+        try:
+            import skimage.measure  # noqa: F401  (the reference's own dependency for this step)
+            backend = "skimage"
+        except ImportError:
+            backend = "gpu"
+    if backend == "gpu":
+        # hold_mc_*: outward normals (towards increasing SDF); normals / values of the skimage tuple are not produced
+        dev = torch.device("cuda", ctx.device)
+        v, f = marching_cubes(ctx, torch.as_tensor(grid, device=dev), level_set)
+        verts_mc = ((v.cpu().numpy() / res - 0.5) * 1.1) * gt_scale + gt_center
+        faces = f.cpu().numpy().astype(np.int64)
+        return largest_component(verts_mc, faces) if keep_largest else (verts_mc, faces, None, None)
+    from skimage import measure
+
     mc = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
     verts_mc, faces, normals, values = mc(volume=grid, gradient_direction="ascent", level=level_set)
     verts_mc = (verts_mc / res - 0.5) * 1.1

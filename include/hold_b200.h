@@ -187,6 +187,18 @@ int hold_mise_create(hold_ctx* ctx, int resolution_0, int depth, float threshold
 int hold_mise_query(hold_mise* h, int32_t* coords, int capacity, int* n_points, void* stream);
 int hold_mise_update(hold_mise* h, const float* values, int n_values, void* stream);
 int hold_mise_to_dense(hold_mise* h, float* out, void* stream);
+
+/* Marching cubes on the dense value grid vol [n0,n1,n2] (C order) — the last step of generate_mesh (utils/meshing.py:51, which calls
+ * skimage.measure.marching_cubes_lewiner; skimage is absent from this image, so this is a classic case-table marching cubes whose
+ * tables are DERIVED (tools/gen_mc_tables.py), pinned to oracle/marching_cubes.py bit for bit and to geometric properties, not to
+ * Lewiner's triangulation).  A node is inside when value < level; one vertex per grid edge whose ends differ, at lower_end +
+ * (level - v0) / (v1 - v0), index coordinates; normals (right-hand rule) towards increasing values.
+ *   hold_mc_mark: edge_flags [n0*n1*n2, 3] int32 (vertex on the edge from node along axis?), cell_ntri [(n0-1)(n1-1)(n2-1)] int32.
+ *   The caller forms the exclusive scans edge_vid / cell_off (int64) of both arrays; their totals size verts [Nv,3] and faces [Nt,3].
+ *   hold_mc_emit: writes the vertices and the faces (vertex ids) in scan order. */
+int hold_mc_mark(hold_ctx* ctx, int n0, int n1, int n2, const float* vol, float level, int32_t* edge_flags, int32_t* cell_ntri, void* stream);
+int hold_mc_emit(hold_ctx* ctx, int n0, int n1, int n2, const float* vol, float level, const int32_t* edge_flags, const int64_t* edge_vid,
+                 const int64_t* cell_off, float* verts, int32_t* faces, void* stream);
 int hold_mise_destroy(hold_mise* h);
 /* a17: ObjectModel.forward (model/obj/object_model.py:29-70). */
 int hold_object_tf(hold_ctx* ctx, int B, const float* rot /*[B,3]*/, const float* trans /*[B,3]*/,
