@@ -1,7 +1,7 @@
 """Marching cubes on the GPU (hold_mc_mark / hold_mc_emit, hold_b200.meshing.marching_cubes) against its numpy restatement
 (oracle/marching_cubes.py; pinned by tests/test_cpu_mc.py to geometric properties and, through mc_phases.h compiled on the host, to
-the kernels' own code): vertices bit for bit, faces exactly; generate_mesh(backend="gpu") on a node's SDF gives one closed,
-outward-oriented component."""
+the kernels' own code): vertices bit for bit, faces exactly; generate_mesh(backend="gpu") on an analytic SDF gives one closed,
+outward-oriented component of the right volume."""
 import numpy as np
 import pytest
 import torch
