@@ -311,15 +311,22 @@ class Node(nn.Module):
         [0]*start + linspace(0, 6, end - start) and advances once per training forward (step_embedding).  Hands and the background
         use the plain Fourier embedder (model/*/specs.py), whose step() does nothing."""
         assert self.kind == "object", "only the object's ImplicitNet uses the BARF embedder (model/obj/specs.py:10)"
-        self._barf = BarfSchedule(6, 3, start, end)
-        self.barf_weights = self._barf.weights().to(self.density.beta.device)
+        dev = self.density.beta.device
+        sched = BarfSchedule(6, 3, start, end)
+        # the whole schedule as a device table + a device-side counter; the weights the kernels read live in ONE persistent buffer
+        # that step_embedding refreshes in place: no host->device copy per step, and a step captured as a CUDA graph
+        # (TrainStep.capture) keeps advancing the schedule on replay
+        self._barf_table = sched.table().to(dev)
+        self._barf_it = torch.zeros((), dtype=torch.int64, device=dev)
+        self._barf = sched
+        self.barf_weights = self._barf_table[0].clone()
 
     def step_embedding(self):
         """Node.step_embedding (node.py:108-109)."""
-        sched = getattr(self, "_barf", None)
-        if sched is not None:
-            sched.step()
-            self.barf_weights = sched.weights().to(self.density.beta.device)
+        if getattr(self, "_barf", None) is not None and self.barf_weights is not None:
+            self._barf.step()      # host mirror of the counter (bookkeeping only)
+            self._barf_it.add_(1).clamp_(max=self._barf_table.shape[0] - 1)
+            self.barf_weights.copy_(self._barf_table.index_select(0, self._barf_it.reshape(1))[0])
 
     def eval(self):
         """BarfEmbedder.eval(): no_barf = True -> all frequencies pass (embedders.py:124-125, render.py:43-47)."""
@@ -448,6 +455,16 @@ class BarfSchedule:
 
     def step(self):
         self.alpha_iter = min(self.alpha_iter + 1, len(self.alphas) - 1)
+
+    def table(self):
+        """[len(alphas), D + 2 L D]: the weights of every iteration."""
+        keep = self.alpha_iter
+        rows = []
+        for it in range(len(self.alphas)):
+            self.alpha_iter = it
+            rows.append(self.weights())
+        self.alpha_iter = keep
+        return torch.stack(rows)
 
     def weights(self):
         ak = self.alphas[self.alpha_iter] - torch.arange(self.L, dtype=torch.float32)
